@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the LIVE reference.
+
+Run in the authoring container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+It imports the unmodified reference from /root/reference (read-only; numba's cache is
+redirected to a temp dir), drives `VecMinesweeper` (minesweeper/env.py:379-517),
+`flood_fill_reveal` (minesweeper/env_numba.py:16-77) and its pure-Python twin
+(env.py:217-244), `RolloutBuffer.compute_gae` (minesweeper/buffers.py:78-94) and the
+real `collect_rollout` (train_rl.py:155-289) on seeded inputs, and records inputs,
+the mine layouts the reference drew (captured by wrapping -- not editing --
+`MinesweeperEnv._place_mines_safe`, env.py:280-312) and every output.
+
+Everything boolean / {0.0,1.0}-valued is stored bit-packed (np.packbits, little bit
+order over the flattened array) after asserting that it really only holds 0/1.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+REF = os.environ.get("MSW_REFERENCE", "/root/reference")
+os.environ.setdefault("NUMBA_CACHE_DIR", tempfile.mkdtemp(prefix="numba_cache_"))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from minesweeper import env as ref_env  # noqa: E402
+from minesweeper.buffers import RolloutBuffer  # noqa: E402
+from minesweeper.env import EnvConfig, MinesweeperEnv, VecMinesweeper  # noqa: E402
+from minesweeper.env_numba import HAS_ENV_NUMBA, flood_fill_reveal  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+assert HAS_ENV_NUMBA, "fixtures must come from the numba flood fill (env_numba.py)"
+
+
+def pack(a: np.ndarray) -> np.ndarray:
+    a = np.asarray(a)
+    u = a.astype(np.uint8)
+    assert np.array_equal(u.astype(a.dtype), a) and u.max(initial=0) <= 1, "not a 0/1 array"
+    return np.packbits(u.reshape(a.shape[0], -1), axis=1, bitorder="little")
+
+
+class LayoutRecorder:
+    """Wraps MinesweeperEnv._place_mines_safe and logs every layout it produces."""
+
+    def __init__(self):
+        self.log = []          # (env object, mine_mask copy)
+        self._orig = MinesweeperEnv._place_mines_safe
+
+    def __enter__(self):
+        rec, orig = self, self._orig
+
+        def wrapped(env, first_click_rc):
+            orig(env, first_click_rc)
+            rec.log.append((env, env.mine_mask.copy()))
+
+        MinesweeperEnv._place_mines_safe = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        MinesweeperEnv._place_mines_safe = self._orig
+
+    def drain(self, index_of):
+        out = [(index_of[id(e)], m) for e, m in self.log]
+        self.log = []
+        return out
+
+
+OUTCOME = {None: 0, "win": 1, "loss": 2}
+
+
+def run_env_case(name, cfg: EnvConfig, N: int, T: int, policy: str, seed: int):
+    """policy: 'valid' | 'any' | 'win' (scripted: click every safe cell)."""
+    rng = np.random.default_rng(seed + 1000)
+    HW = cfg.H * cfg.W
+    with LayoutRecorder() as rec:
+        vec = VecMinesweeper(N, cfg, seed=seed)
+        index_of = {id(e): i for i, e in enumerate(vec.envs)}
+        batch = vec.reset()
+        assert not rec.log
+        obs0, mask0 = batch["obs"], batch["action_mask"]
+        perm = np.stack([rng.permutation(HW) for _ in range(N)])   # per-env click order ('win')
+        acts, place_t, place_i, place_bits = [], [], [], []
+        rec_obs, rec_mask, rec_rew, rec_done, rec_outcome = [], [], [], [], []
+        rec_new, rec_step, rec_frac = [], [], []
+        st_rev, st_mine, st_cnt, st_first, st_stepc = [], [], [], [], []
+        lab, val = [], []
+        mask = mask0
+        for t in range(T):
+            if policy == "valid":
+                s = rng.random(mask.shape)
+                s[~mask] = -1.0
+                a = s.argmax(1).astype(np.int64)
+            elif policy == "any":
+                a = rng.integers(-3 * HW, 3 * HW, size=N, dtype=np.int64)
+            elif policy == "win":
+                a = np.zeros(N, np.int64)
+                for i, e in enumerate(vec.envs):
+                    if not e.first_click_done:
+                        a[i] = int(rng.integers(0, HW))
+                    else:
+                        safe_hidden = (~e.mine_mask & ~e.revealed).reshape(-1)
+                        order = perm[i]
+                        a[i] = int(order[np.argmax(safe_hidden[order])])
+            else:
+                raise ValueError(policy)
+            batch, rew, done, infos = vec.step(a.astype(np.int32) if policy != "any" else a)
+            for i, m in rec.drain(index_of):
+                place_t.append(t); place_i.append(i); place_bits.append(m.reshape(-1))
+            acts.append(a)
+            rec_obs.append(pack(batch["obs"])); rec_mask.append(pack(batch["action_mask"]))
+            rec_rew.append(rew.copy()); rec_done.append(done.copy())
+            rec_outcome.append(np.array([OUTCOME[o] for o in infos["outcome"]], np.int8))
+            rec_new.append(np.array([x["last_new_reveals"] for x in infos["aux"]], np.int32))
+            rec_step.append(np.array([x["step"] for x in infos["aux"]], np.int32))
+            rec_frac.append(np.array([x["revealed_frac"] for x in infos["aux"]], np.float64))
+            assert infos["done"] == [bool(d) for d in done]
+            st_rev.append(pack(np.stack([e.revealed for e in vec.envs])))
+            st_mine.append(pack(np.stack([e.mine_mask for e in vec.envs])))
+            st_cnt.append(np.stack([e.adjacent_counts for e in vec.envs]).reshape(N, -1).copy())
+            st_first.append(np.array([e.first_click_done for e in vec.envs], bool))
+            st_stepc.append(np.array([e.step_count for e in vec.envs], np.int32))
+            # auxiliary maps exactly as train_rl.py:205-212 derives them from vec.envs
+            L = np.zeros((N, cfg.H, cfg.W), np.float32)
+            V = np.zeros((N, cfg.H, cfg.W), bool)
+            for i, e in enumerate(vec.envs):
+                if e.first_click_done:
+                    np.copyto(L[i], e.mine_mask, casting="unsafe")
+                    np.logical_and(~e.revealed, ~e.flags, out=V[i])
+            lab.append(pack(L)); val.append(pack(V))
+            mask = batch["action_mask"]
+    place_bits = np.stack(place_bits) if place_bits else np.zeros((0, HW), bool)
+    rew = np.stack(rec_rew)
+    done = np.stack(rec_done)
+    out = dict(
+        H=cfg.H, W=cfg.W, mine_count=cfg.mine_count, safe=int(cfg.guarantee_safe_neighborhood),
+        win_reward=cfg.win_reward, loss_reward=cfg.loss_reward, step_penalty=cfg.step_penalty,
+        N=N, T=T, seed=seed,
+        obs0=pack(obs0), mask0=pack(mask0),
+        actions=np.stack(acts),
+        place_t=np.array(place_t, np.int32), place_i=np.array(place_i, np.int32),
+        place_bits=np.packbits(place_bits.astype(np.uint8), axis=1, bitorder="little"),
+        obs=np.stack(rec_obs), mask=np.stack(rec_mask), rewards=rew, dones=done,
+        outcome=np.stack(rec_outcome), new_reveals=np.stack(rec_new), step=np.stack(rec_step),
+        revealed_frac=np.stack(rec_frac),
+        st_revealed=np.stack(st_rev), st_mine=np.stack(st_mine), st_counts=np.stack(st_cnt),
+        st_first=np.stack(st_first), st_step_count=np.stack(st_stepc),
+        mine_labels=np.stack(lab), mine_valid=np.stack(val),
+    )
+    np.savez_compressed(os.path.join(OUT, f"env_{name}.npz"), **out)
+    oc = np.stack(rec_outcome)
+    print(f"env_{name}: N={N} T={T} episodes={int(done.sum())} wins={int((oc == 1).sum())} "
+          f"losses={int((oc == 2).sum())} placements={len(place_t)} "
+          f"distinct_rewards={sorted(set(rew.view(np.uint32).reshape(-1).tolist()))}")
+
+
+def run_floodfill_case():
+    """Arbitrary (mines, revealed, flags, start) boards -- including non-empty flags,
+    which the hot path never produces -- through BOTH reference flood fills."""
+    rng = np.random.default_rng(7)
+    recs = []
+    shapes = [(16, 16), (16, 30), (30, 16), (9, 9), (8, 8), (5, 7), (1, 12), (32, 32), (3, 3)]
+    for H, W in shapes:
+        inputs, outs_rev, outs_n = [], [], []
+        for k in range(60):
+            dens = rng.choice([0.0, 0.05, 0.12, 0.16, 0.3])
+            mines = rng.random((H, W)) < dens
+            revealed = rng.random((H, W)) < rng.choice([0.0, 0.1, 0.5])
+            flags = rng.random((H, W)) < rng.choice([0.0, 0.0, 0.1, 0.3])
+            r, c = int(rng.integers(0, H)), int(rng.integers(0, W))
+            env = MinesweeperEnv(EnvConfig(H=H, W=W, mine_count=0))
+            counts = env._compute_adjacent_counts(mines).copy()
+            rev_nb = revealed.copy()
+            n_nb = int(flood_fill_reveal(rev_nb, flags, mines, counts, r, c))
+            # the pure-Python twin (env.py:217-244); it does not early-out on a mine start,
+            # so compare only where the numba contract (start not a mine) is met by step().
+            env.mine_mask[:] = mines; env.adjacent_counts[:] = counts
+            env.revealed[:] = revealed; env.flags[:] = flags
+            n_py = env._reveal_with_flood_fill_python(r, c)
+            if not mines[r, c]:
+                assert n_py == n_nb and np.array_equal(env.revealed, rev_nb)
+            inputs.append(np.concatenate([mines.reshape(-1), revealed.reshape(-1), flags.reshape(-1)]))
+            outs_rev.append(rev_nb.reshape(-1)); outs_n.append((r, c, n_nb))
+        recs.append((H, W, np.stack(inputs), np.stack(outs_rev), np.array(outs_n, np.int32)))
+    out = {"shapes": np.array([(h, w) for h, w, *_ in recs], np.int32)}
+    for h, w, i, o, n in recs:
+        out[f"in_{h}x{w}"] = np.packbits(i.astype(np.uint8), axis=1, bitorder="little")
+        out[f"rev_{h}x{w}"] = np.packbits(o.astype(np.uint8), axis=1, bitorder="little")
+        out[f"rcn_{h}x{w}"] = n
+    np.savez_compressed(os.path.join(OUT, "floodfill.npz"), **out)
+    print("floodfill:", {f"{h}x{w}": int(n[:, 2].sum()) for h, w, _, _, n in recs})
+
+
+def run_gae_cases():
+    out = {}
+    names = []
+
+    def case(name, T, N, p_done, gamma, lam, seed, lv_dtype=torch.float32, pattern=None):
+        g = torch.Generator().manual_seed(seed)
+        consts = torch.tensor([-1e-4, -1.0 - 1e-4, 1.0 - 1e-4], dtype=torch.float64).float()
+        buf = RolloutBuffer(N, T, (1, 1, 1), 1, torch.device("cpu"))
+        dones = torch.rand((T, N), generator=g) < p_done
+        if pattern == "all":
+            dones[:] = True
+        elif pattern == "none":
+            dones[:] = False
+        elif pattern == "last":
+            dones[:] = False; dones[-1] = True
+        rewards = torch.where(dones, consts[torch.randint(1, 3, (T, N), generator=g)], consts[0])
+        if pattern == "gauss":
+            rewards = torch.randn((T, N), generator=g)
+        values = 0.5 * torch.randn((T, N), generator=g)
+        last_values = (0.5 * torch.randn((N,), generator=g)).to(lv_dtype)
+        buf.rewards[:] = rewards.reshape(-1); buf.values[:] = values.reshape(-1)
+        buf.dones[:] = dones.reshape(-1)
+        buf.compute_gae(last_values, gamma=gamma, lam=lam)
+        names.append(name)
+        out[f"{name}_rewards"] = rewards.numpy(); out[f"{name}_values"] = values.numpy()
+        out[f"{name}_dones"] = dones.numpy()
+        out[f"{name}_last_values"] = last_values.float().numpy()
+        out[f"{name}_lv_is_fp16"] = np.array(lv_dtype == torch.float16)
+        out[f"{name}_gamma_lam"] = np.array([gamma, lam], np.float64)
+        out[f"{name}_adv"] = buf.advantages.view(T, N).numpy().copy()
+        out[f"{name}_ret"] = buf.returns.view(T, N).numpy().copy()
+
+    case("c3like", 128, 96, 0.15, 0.995, 0.95, 0)
+    case("short", 1, 33, 0.3, 0.995, 0.95, 1)
+    case("t2", 2, 7, 0.5, 0.99, 0.9, 2)
+    case("alldone", 16, 40, 0.0, 0.995, 0.95, 3, pattern="all")
+    case("nodone", 64, 40, 0.0, 0.995, 0.95, 4, pattern="none")
+    case("lastdone", 32, 40, 0.0, 0.995, 0.95, 5, pattern="last")
+    case("gauss", 200, 65, 0.1, 0.9, 0.8, 6, pattern="gauss")
+    case("lam1", 50, 31, 0.05, 1.0, 1.0, 7, pattern="gauss")
+    case("lam0", 50, 31, 0.05, 0.97, 0.0, 8, pattern="gauss")
+    case("fp16_last", 64, 48, 0.15, 0.995, 0.95, 9, lv_dtype=torch.float16)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "gae.npz"), **out)
+    print("gae:", names)
+
+
+def run_rollout_case():
+    """The real collect_rollout (train_rl.py:155-289) with a stub policy: pins the
+    buffer-write protocol (time alignment of obs/mask/labels vs reward/done) and the
+    auxiliary mine_labels / mine_valid maps."""
+    import train_rl  # noqa: WPS433  (reference script, imported as a module)
+
+    class Stub(torch.nn.Module):
+        def __init__(self, HW):
+            super().__init__()
+            self.HW = HW
+            self.g = torch.Generator().manual_seed(5)
+
+        def forward(self, obs, return_mine=False):
+            B = obs.shape[0]
+            logits = torch.randn((B, self.HW), generator=self.g)
+            value = torch.randn((B,), generator=self.g)
+            if return_mine:
+                return logits, value, torch.zeros((B, 1, obs.shape[-2], obs.shape[-1]))
+            return logits, value
+
+    cfg = EnvConfig(H=16, W=16, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    N, T = 24, 48
+    torch.manual_seed(11)
+    with LayoutRecorder() as rec:
+        vec = VecMinesweeper(N, cfg, seed=3)
+        index_of = {id(e): i for i, e in enumerate(vec.envs)}
+        # step-resolved layout log: wrap vec.step to know the step index of each placement
+        place_t, place_i, place_bits = [], [], []
+        tcount = [0]
+        orig_step = vec.step
+
+        def step_logged(actions):
+            r = orig_step(actions)
+            for i, m in rec.drain(index_of):
+                place_t.append(tcount[0]); place_i.append(i); place_bits.append(m.reshape(-1))
+            tcount[0] += 1
+            return r
+
+        vec.step = step_logged
+        buf, aux = train_rl.collect_rollout(vec, Stub(256), T, torch.device("cpu"),
+                                            aux_mine_weight=0.05, aux_mine_calib_weight=0.01)
+    last_values = aux["last_values"].detach().float()
+    buf.compute_gae(last_values, gamma=0.995, lam=0.95)
+    out = dict(
+        H=16, W=16, mine_count=40, safe=1, win_reward=1.0, loss_reward=-1.0, step_penalty=1e-4,
+        N=N, T=T,
+        actions=buf.actions.view(T, N).numpy(),
+        place_t=np.array(place_t, np.int32), place_i=np.array(place_i, np.int32),
+        place_bits=np.packbits(np.stack(place_bits).astype(np.uint8), axis=1, bitorder="little"),
+        obs=pack(buf.obs.numpy()).reshape(T, N, -1), mask=pack(buf.action_mask.numpy()).reshape(T, N, -1),
+        rewards=buf.rewards.view(T, N).numpy(), dones=buf.dones.view(T, N).numpy(),
+        values=buf.values.view(T, N).numpy(), logp=buf.logp.view(T, N).numpy(),
+        mine_labels=pack(buf.mine_labels.numpy()).reshape(T, N, -1),
+        mine_valid=pack(buf.mine_valid.numpy()).reshape(T, N, -1),
+        last_values=last_values.numpy(),
+        adv=buf.advantages.view(T, N).numpy(), ret=buf.returns.view(T, N).numpy(),
+    )
+    np.savez_compressed(os.path.join(OUT, "rollout_16x16x40.npz"), **out)
+    print(f"rollout: N={N} T={T} dones={int(buf.dones.sum())} placements={len(place_t)}")
+
+
+def main():
+    std = dict(guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    run_env_case("16x16x40_valid", EnvConfig(H=16, W=16, mine_count=40, **std), 48, 96, "valid", 0)
+    run_env_case("16x16x40_any", EnvConfig(H=16, W=16, mine_count=40, **std), 48, 96, "any", 1)
+    run_env_case("16x16x40_win", EnvConfig(H=16, W=16, mine_count=40, **std), 8, 220, "win", 2)
+    run_env_case("16x30x99_valid", EnvConfig(H=16, W=30, mine_count=99, **std), 32, 64, "valid", 3)
+    run_env_case("16x30x99_win", EnvConfig(H=16, W=30, mine_count=99, **std), 4, 260, "win", 4)
+    run_env_case("8x8x10_default", EnvConfig(), 32, 64, "valid", 5)
+    run_env_case("4x4x8_fallback", EnvConfig(H=4, W=4, mine_count=8), 32, 48, "any", 6)
+    run_env_case("5x7x6_nosafe", EnvConfig(H=5, W=7, mine_count=6, guarantee_safe_neighborhood=False,
+                                           win_reward=2.5, loss_reward=-0.75, step_penalty=0.01),
+                 32, 64, "valid", 7)
+    run_env_case("32x32x150_valid", EnvConfig(H=32, W=32, mine_count=150), 8, 48, "valid", 8)
+    run_env_case("30x16x99_win", EnvConfig(H=30, W=16, mine_count=99), 4, 260, "win", 9)
+    run_floodfill_case()
+    run_gae_cases()
+    run_rollout_case()
+
+
+if __name__ == "__main__":
+    main()
