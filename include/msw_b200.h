@@ -1,0 +1,179 @@
+/*
+ * msw_b200.h -- C ABI of the B200-native minesweeper-ppo rollout hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI
+ * layer -- its boundary is the duck-typed Python API of minesweeper/env.py and
+ * minesweeper/buffers.py -- so each entry point below names the reference
+ * function it replaces; minesweeper_ppo_b200/{env,buffers}.py bind them with
+ * ctypes behind the reference's own class and method names.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - "device" pointers are CUDA device memory owned by the caller (PyTorch's
+ *     caching allocator); the library never allocates or frees device memory
+ *     and keeps no global state except a thread-local last-error string.
+ *   - Every device entry point is an asynchronous, stream-ordered launch on
+ *     `stream` (a cudaStream_t passed as void*); no host synchronisation
+ *     inside.  The *_host entry points take pinned HOST buffers, copy in/out on
+ *     `stream` and synchronise it before returning.
+ *   - Return value: 0 on success, MSW_ERR_* (>0) on bad arguments, or a
+ *     negated cudaError_t (<0) when the CUDA runtime reports an error;
+ *     msw_last_error() describes the most recent failure on this thread.
+ *   - There is no CPU fallback anywhere behind this interface.
+ *
+ * Board layout: a board is a flat bitstring of H*W cells, cell (r,c) at bit
+ * r*W+c, stored as msw_words_per_board(H,W) little-endian uint32 words
+ * (== np.packbits(board.reshape(-1), bitorder="little") padded to 4 bytes).
+ * Limits: 1 <= W <= 32, 1 <= H*W <= 1024, 0 <= mine_count <= H*W-1.
+ */
+#ifndef MSW_B200_H
+#define MSW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSW_VERSION 1
+#define MSW_OBS_CHANNELS 10        /* env.py:79-85: revealed + one-hot counts 0..8 */
+#define MSW_MAX_CELLS 1024
+
+enum {
+    MSW_OK = 0,
+    MSW_ERR_BAD_SHAPE = 1,         /* H, W, mine_count or n out of range */
+    MSW_ERR_NULL = 2,              /* required pointer is NULL */
+    MSW_ERR_ALIGN = 3,             /* pointer not aligned for vector stores */
+    MSW_ERR_ARG = 4                /* inconsistent arguments */
+};
+
+/* Static description of one shard of environments; mirrors EnvConfig
+ * (minesweeper/env.py:19-30) plus what VecMinesweeper.__init__ (env.py:382-403)
+ * derives from `seed`. */
+typedef struct msw_env_desc {
+    int32_t H, W;
+    int32_t mine_count;
+    int32_t safe_nbhd;             /* EnvConfig.guarantee_safe_neighborhood */
+    /* Rewards pre-rounded to fp32 exactly as the reference does: accumulated in
+     * float64 (env.py:110,128,137,142) then stored into a float32 array
+     * (env.py:483,501).  step = -step_penalty; loss = loss_reward-step_penalty;
+     * win = win_reward-step_penalty. */
+    float reward_step, reward_loss, reward_win;
+    int32_t reserved;
+    uint64_t seed;                 /* key of the counter-based board sampler */
+    int64_t env_id_base;           /* global id of env 0 (multi-GPU sharding) */
+} msw_env_desc;
+
+/* Persistent per-env state (device).  Replaces the MinesweeperEnv attributes
+ * mine_mask / revealed / flags / first_click_done / step_count /
+ * _last_new_reveals (env.py:68-75); adjacent_counts is recomputed from
+ * `mines` on the fly and never stored. */
+typedef struct msw_state {
+    uint32_t *mines;               /* [n][wpb] */
+    uint32_t *revealed;            /* [n][wpb] */
+    uint32_t *flags;               /* [n][wpb]; NULL == no flags anywhere (hot path) */
+    int32_t  *meta;                /* [n][4]: first_click_done, step_count,
+                                      episode_idx (sampler counter), last_new_reveals;
+                                      16-byte aligned */
+} msw_state;
+
+/* Outputs of reset / step / encode (device).  obs must be 16-byte aligned when
+ * H*W % 4 == 0 (vector store path); nullable members may be NULL. */
+typedef struct msw_encode_out {
+    float   *obs;                  /* [n][10][H][W] f32          env.py:172-192 */
+    uint8_t *mask;                 /* [n][H*W] bool              env.py:194-196 */
+    float   *mine_labels;          /* nullable [n][H][W] f32     train_rl.py:205-212 */
+    uint8_t *mine_valid;           /* nullable [n][H][W] bool    train_rl.py:205-212 */
+} msw_encode_out;
+
+typedef struct msw_step_io {
+    const int32_t *actions32;      /* [n]; exactly one of actions32/actions64 */
+    const int64_t *actions64;      /* [n] */
+    const uint32_t *inject_bits;   /* nullable [n][wpb]: layouts for parity tests */
+    const uint8_t  *inject_sel;    /* nullable [n]: 1 => env takes inject_bits when it
+                                      places mines in this step */
+    float   *reward;               /* [n] f32   env.py:501 */
+    uint8_t *done;                 /* [n] bool  env.py:502 */
+    int8_t  *outcome;              /* nullable [n]: 0 none, 1 win, 2 loss  env.py:493 */
+    int32_t *new_reveals;          /* nullable [n]: aux.last_new_reveals (pre-reset) */
+    int32_t *step;                 /* nullable [n]: aux.step (pre-reset) */
+    int32_t *revealed_count;       /* nullable [n]: popcount(revealed) (pre-reset);
+                                      revealed_frac = count / (H*W), env.py:165 */
+    msw_encode_out enc;            /* observation of the post-(auto-)reset state */
+} msw_step_io;
+
+int msw_version(void);
+const char *msw_last_error(void);
+int msw_words_per_board(int32_t H, int32_t W);
+
+/* VecMinesweeper.reset (env.py:468-477) -> MinesweeperEnv.reset (env.py:87-101):
+ * zero all state, bump the sampler counter, emit the all-zero observation and
+ * all-true mask.  No mines are placed at reset. */
+int msw_reset(const msw_env_desc *desc, const msw_state *st, int64_t n,
+              const msw_encode_out *out, void *stream);
+
+/* VecMinesweeper.step (env.py:479-511) with everything under it fused into one
+ * launch: MinesweeperEnv.step (env.py:103-152), _place_mines_safe (:280-312),
+ * _compute_adjacent_counts (:314-335), flood_fill_reveal (env_numba.py:16-77),
+ * auto-reset (:497-498), _build_obs (:172-192), _compute_action_mask (:194-196),
+ * _build_aux (:163-170) and the aux label extraction of train_rl.py:203-219. */
+int msw_step(const msw_env_desc *desc, const msw_state *st, const msw_step_io *io,
+             int64_t n, void *stream);
+
+/* _build_obs / _compute_action_mask of the current state without stepping. */
+int msw_encode(const msw_env_desc *desc, const msw_state *st, int64_t n,
+               const msw_encode_out *out, void *stream);
+
+/* Expands the bitboards into the reference's per-cell arrays for the
+ * `vec.envs[i]` compatibility views (env.py:68-71): bool [n][H*W] each and
+ * adjacent_counts u8 [n][H*W] (env.py:314-335).  Any output may be NULL. */
+int msw_unpack_state(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                     uint8_t *mine, uint8_t *revealed, uint8_t *flags,
+                     uint8_t *counts, void *stream);
+
+/* Synthetic action source for benchmarks/tests: a
+ * uniformly random unrevealed cell per env (valid_only=1; 0 if none) or a
+ * uniformly random cell (valid_only=0).  Writes whichever of a32/a64 is
+ * non-NULL. */
+int msw_random_actions(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                       uint64_t seed, uint32_t step_index, int32_t valid_only,
+                       int32_t *a32, int64_t *a64, void *stream);
+
+/* RolloutBuffer.compute_gae (buffers.py:78-94) over time-major [T][N] fp32
+ * with unfused IEEE multiplies/adds in the reference's order.  gamma_f32 and
+ * gamma_lam_f32 are float(gamma) and float(gamma*lam) (product in float64).
+ * last_values_prescaled != 0: `last_values` already holds gamma*last_value as
+ * the caller's tensor dtype rounds it (the reference's bootstrap value is fp16
+ * under CUDA autocast, train_rl.py:272-277, so `gamma * next_value` at t=T-1 is
+ * rounded to fp16 before it is promoted, buffers.py:88-90); the kernel then
+ * skips that one multiply. */
+int msw_gae(const float *rewards, const float *values, const uint8_t *dones,
+            const float *last_values, float *advantages, float *returns,
+            int64_t T, int64_t N, float gamma_f32, float gamma_lam_f32,
+            int32_t last_values_prescaled, void *stream);
+
+/* Host-buffer form of msw_step for callers that keep the reference's NumPy
+ * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):
+ * `h_actions32` and every non-NULL h_* output are pinned host buffers; `io`
+ * holds the device staging buffers (same meaning as msw_step; io->actions32
+ * is the device staging buffer for the actions).  Copies actions in, runs the
+ * step, copies the requested outputs back and synchronises `stream`. */
+typedef struct msw_host_out {
+    float   *obs;                  /* nullable */
+    uint8_t *mask;                 /* nullable */
+    float   *reward;               /* nullable */
+    uint8_t *done;                 /* nullable */
+    int8_t  *outcome;              /* nullable */
+    int32_t *new_reveals;          /* nullable */
+    int32_t *step;                 /* nullable */
+    int32_t *revealed_count;       /* nullable */
+} msw_host_out;
+
+int msw_step_host(const msw_env_desc *desc, const msw_state *st,
+                  const msw_step_io *io, const int32_t *h_actions32,
+                  const msw_host_out *h_out, int64_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSW_B200_H */

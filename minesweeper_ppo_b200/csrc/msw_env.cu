@@ -1,0 +1,601 @@
+// msw_env.cu -- vectorised Minesweeper environment kernels for sm_100a and
+// their C-ABI entry points (include/msw_b200.h).
+//
+// One warp owns one board at a time (boards are independent: env.py:491-505
+// touches only envs[i]).  The whole of VecMinesweeper.step -- action decode,
+// first-click-safe mine placement, adjacency counts, flood-fill reveal, win /
+// loss, reward, auto-reset, observation planes, action mask and the auxiliary
+// mine label / valid maps -- is ONE kernel: the ~100 B of board state lives in
+// registers between the step logic and the encoder, and the only HBM traffic
+// that matters is the 10.5 KB (16x16) of fp32 observation + mask each warp
+// streams out with 128-bit stores.  The kernel is HBM-write bound by design;
+// the flood fill is latency-bound but hidden behind other warps' stores.
+#include "../../include/msw_b200.h"
+#include "msw_common.cuh"
+#include "msw_error.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace msw {
+
+struct EnvParams {
+    int H, W, HW, wpb;
+    int mine_count, safe;
+    float r_step, r_loss, r_win;
+    uint32_t k0, k1;                 // sampler key (seed)
+    uint32_t thresh16;               // 65536 % HW (Lemire rejection threshold)
+    long long env_id_base;
+    long long n;
+    // state
+    uint32_t *mines, *revealed, *flags;
+    int4 *meta;
+    // step inputs
+    const int32_t *a32;
+    const long long *a64;
+    const uint32_t *inj_bits;
+    const uint8_t *inj_sel;
+    // step outputs
+    float *reward;
+    uint8_t *done;
+    int8_t *outcome;
+    int32_t *new_reveals, *step, *rcount;
+    // encode outputs
+    float *obs;
+    uint8_t *mask;
+    float *labels;
+    uint8_t *valid;
+    // per-lane geometry
+    uint32_t g_valid[32], g_notcol0[32], g_notlast[32];
+};
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
+
+// ---------------------------------------------------------------------------
+// First-click-safe placement (replaces env.py:280-312).  Forbidden set and the
+// tiny-board fallback follow the reference; the subset itself is drawn with the
+// counter-based sampler of DESIGN.md (NumPy's PCG64 stream is outside the
+// parity contract): 16-bit Lemire draws over all cells in Philox stream order,
+// rejecting forbidden / already chosen cells -- exactly uniform over
+// mine_count-subsets of the allowed cells.  All lanes walk the same draw
+// sequence; lane l generates Philox block (32*batch + l), so one Philox call per
+// lane yields 256 draws for the warp.
+// ---------------------------------------------------------------------------
+template <int CW, int CHW>
+__device__ __noinline__ uint32_t sample_mines(const EnvParams &p, long long env_id, uint32_t episode,
+                                              uint32_t startmask, int lane, const Geo &g)
+{
+    const int W = CW ? CW : p.W;
+    const int HW = CHW ? CHW : p.HW;
+    const int M = p.mine_count;
+    uint32_t forb = startmask;
+    if (p.safe) forb |= dilate8<CW>(startmask, lane, W, g);          // env.py:288-299
+    int allowed = HW - warp_popc_sum(forb);
+    if (allowed < M) {                                               // env.py:303-307
+        forb = startmask;
+        allowed = HW - 1;
+    }
+    const bool comp = 2 * M > allowed;          // sample the complement when dense
+    const int K = comp ? allowed - M : M;
+    const uint32_t thresh = p.thresh16;
+    const uint32_t id_lo = (uint32_t)(unsigned long long)env_id;
+    const uint32_t id_hi = (uint32_t)((unsigned long long)env_id >> 32);
+
+    uint32_t chosen = 0;
+    int cnt = 0;
+    for (uint32_t batch = 0; cnt < K; ++batch) {
+        uint32_t w[4];
+        philox4x32_10(p.k0, p.k1, id_lo, id_hi, episode, batch * 32u + (uint32_t)lane, w);
+        for (int blk = 0; blk < 32 && cnt < K; ++blk) {
+            uint32_t v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(FULL, w[i], blk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t x = (v[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                const uint32_t m = x * (uint32_t)HW;
+                const uint32_t d = m >> 16;
+                const uint32_t bit = 1u << (d & 31u);
+                const bool ok = (cnt < K) && ((m & 0xFFFFu) >= thresh) && (lane == (int)(d >> 5)) &&
+                                !((forb | chosen) & bit);
+                if (ok) chosen |= bit;
+                cnt += __any_sync(FULL, ok) ? 1 : 0;
+            }
+        }
+    }
+    return comp ? (g.valid & ~forb & ~chosen) : chosen;
+}
+
+// ---------------------------------------------------------------------------
+// Encoder: _build_obs (env.py:172-192), _compute_action_mask (env.py:194-196)
+// and the aux maps of train_rl.py:205-212, from register-resident bitboards.
+// Vector path (HW % 4 == 0): lane handles cells [4q, 4q+4) of every plane, one
+// st.global.cs.v4.f32 per plane -> each warp store covers 512 contiguous bytes.
+// ---------------------------------------------------------------------------
+template <int CW, int CHW>
+__device__ __forceinline__ void encode_board(const EnvParams &p, long long b, int lane, uint32_t R,
+                                             uint32_t M, uint32_t F, int first, const Planes &pl,
+                                             const Geo &g)
+{
+    const int HW = CHW ? CHW : p.HW;
+    const uint32_t Lm = first ? M : 0u;                               // train_rl.py:206-208
+    const uint32_t Vm = first ? (~R & ~F & g.valid) : 0u;             // train_rl.py:209
+    const uint32_t NR = ~R & g.valid;                                 // env.py:195
+    if ((HW & 3) == 0) {
+        const int quads = HW >> 2;
+        float4 *obs_b = p.obs ? reinterpret_cast<float4 *>(p.obs + b * (long long)(MSW_OBS_CHANNELS * HW)) : nullptr;
+        uint32_t *mask_b = p.mask ? reinterpret_cast<uint32_t *>(p.mask + b * (long long)HW) : nullptr;
+        float4 *lab_b = p.labels ? reinterpret_cast<float4 *>(p.labels + b * (long long)HW) : nullptr;
+        uint32_t *val_b = p.valid ? reinterpret_cast<uint32_t *>(p.valid + b * (long long)HW) : nullptr;
+#pragma unroll 2
+        for (int q0 = 0; q0 < quads; q0 += 32) {
+            const int q = q0 + lane;
+            const bool act = q < quads;
+            const int src = (act ? q : 0) >> 3;
+            const int sh = (q & 7) << 2;
+            const uint32_t r4 = (__shfl_sync(FULL, R, src) >> sh) & 15u;
+            const uint32_t a0 = (__shfl_sync(FULL, pl.c0, src) >> sh) & 15u;
+            const uint32_t a1 = (__shfl_sync(FULL, pl.c1, src) >> sh) & 15u;
+            const uint32_t a2 = (__shfl_sync(FULL, pl.c2, src) >> sh) & 15u;
+            const uint32_t a3 = (__shfl_sync(FULL, pl.c3, src) >> sh) & 15u;
+            const uint32_t n4 = (__shfl_sync(FULL, NR, src) >> sh) & 15u;
+            uint32_t l4 = 0, v4 = 0;
+            if (lab_b) l4 = (__shfl_sync(FULL, Lm, src) >> sh) & 15u;
+            if (val_b) v4 = (__shfl_sync(FULL, Vm, src) >> sh) & 15u;
+            if (!act) continue;
+            if (obs_b) {
+                const uint32_t g4 = first ? r4 : 0u;                  // env.py:181
+                float4 *o = obs_b + q;
+                __stcs(o, nib_to_f4(r4));
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const uint32_t m = g4 & ((k & 1) ? a0 : ~a0) & ((k & 2) ? a1 : ~a1) &
+                                       ((k & 4) ? a2 : ~a2) & ((k & 8) ? a3 : ~a3);
+                    __stcs(o + (1 + k) * quads, nib_to_f4(m));
+                }
+            }
+            if (mask_b) __stcs(mask_b + q, nib_to_b4(n4));
+            if (lab_b) __stcs(lab_b + q, nib_to_f4(l4));
+            if (val_b) __stcs(val_b + q, nib_to_b4(v4));
+        }
+    } else {
+        // Scalar path for boards whose planes are not 16-byte multiples (e.g. 5x7, 9x9).
+        const int wpb = (HW + 31) >> 5;
+        float *obs_b = p.obs ? p.obs + b * (long long)(MSW_OBS_CHANNELS * HW) : nullptr;
+        uint8_t *mask_b = p.mask ? p.mask + b * (long long)HW : nullptr;
+        float *lab_b = p.labels ? p.labels + b * (long long)HW : nullptr;
+        uint8_t *val_b = p.valid ? p.valid + b * (long long)HW : nullptr;
+        for (int it = 0; it < wpb; ++it) {
+            const int cell = it * 32 + lane;
+            const uint32_t r = (__shfl_sync(FULL, R, it) >> lane) & 1u;
+            const uint32_t cnt = ((__shfl_sync(FULL, pl.c0, it) >> lane) & 1u) |
+                                 (((__shfl_sync(FULL, pl.c1, it) >> lane) & 1u) << 1) |
+                                 (((__shfl_sync(FULL, pl.c2, it) >> lane) & 1u) << 2) |
+                                 (((__shfl_sync(FULL, pl.c3, it) >> lane) & 1u) << 3);
+            const uint32_t l = (__shfl_sync(FULL, Lm, it) >> lane) & 1u;
+            const uint32_t v = (__shfl_sync(FULL, Vm, it) >> lane) & 1u;
+            if (cell >= HW) continue;
+            if (obs_b) {
+                obs_b[cell] = r ? 1.0f : 0.0f;
+                for (int k = 0; k < 9; ++k)
+                    obs_b[(1 + k) * HW + cell] = (first && r && cnt == (uint32_t)k) ? 1.0f : 0.0f;
+            }
+            if (mask_b) mask_b[cell] = (uint8_t)(r ^ 1u);
+            if (lab_b) lab_b[cell] = l ? 1.0f : 0.0f;
+            if (val_b) val_b[cell] = (uint8_t)v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The fused env kernel.  MODE_STEP: VecMinesweeper.step (env.py:479-511);
+// MODE_RESET: VecMinesweeper.reset (env.py:468-477); MODE_ENCODE: observation
+// of the current state.  CW/CHW != 0 specialise the board shape at compile time.
+// ---------------------------------------------------------------------------
+template <int MODE, int CW, int CHW>
+__global__ void __launch_bounds__(256, 4) env_kernel(const __grid_constant__ EnvParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int W = CW ? CW : p.W;
+    const int HW = CHW ? CHW : p.HW;
+    const int wpb = (HW + 31) >> 5;
+    const long long warps_per_block = blockDim.x >> 5;
+    const long long total_warps = (long long)gridDim.x * warps_per_block;
+    Geo g;
+    g.valid = p.g_valid[lane];
+    g.notcol0 = p.g_notcol0[lane];
+    g.notlast = p.g_notlast[lane];
+    const bool own = lane < wpb;
+
+    for (long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < p.n; b += total_warps) {
+        uint32_t M = 0, R = 0, F = 0;
+        int4 meta = p.meta[b];          // first_click_done, step_count, episode_idx, last_new_reveals
+        if (MODE != MODE_RESET && own) {
+            M = p.mines[b * wpb + lane];
+            R = p.revealed[b * wpb + lane];
+            if (p.flags) F = p.flags[b * wpb + lane];
+        }
+        int first = meta.x;
+        Planes pl = {0u, 0u, 0u, 0u};
+
+        if (MODE == MODE_RESET) {
+            // env.py:87-95: zero everything; the sampler counter moves on (the reference's
+            // per-env Generator is never re-seeded either, env.py:49).
+            first = 0;
+            if (own) {
+                p.mines[b * wpb + lane] = 0u;
+                p.revealed[b * wpb + lane] = 0u;
+                if (p.flags) p.flags[b * wpb + lane] = 0u;
+            }
+            if (lane == 0) p.meta[b] = make_int4(0, 0, meta.z + 1, 0);
+        } else if (MODE == MODE_ENCODE) {
+            if (first) pl = count_planes<CW>(M, lane, W, g);
+        } else {
+            // ---- action decode: cell = action % (H*W), Python modulo (env.py:104-107)
+            int cell;
+            if (p.a32) {
+                cell = p.a32[b] % HW;
+            } else {
+                const long long a = p.a64[b];
+                cell = (a == (long long)(int)a) ? ((int)a % HW) : (int)(a % (long long)HW);
+            }
+            if (cell < 0) cell += HW;
+            const uint32_t startmask = (lane == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
+
+            int done = 0, outcome = 0, newly = 0;
+            bool mines_dirty = false, reveal_branch = false;
+            if (!__any_sync(FULL, R & startmask)) {                       // env.py:118
+                if (!first) {                                             // env.py:119-122
+                    if (p.inj_sel && p.inj_sel[b])
+                        M = own ? (p.inj_bits[b * wpb + lane] & g.valid) : 0u;
+                    else
+                        M = sample_mines<CW, CHW>(p, p.env_id_base + b, (uint32_t)meta.z, startmask, lane, g);
+                    first = 1;
+                    mines_dirty = true;
+                }
+                pl = count_planes<CW>(M, lane, W, g);                     // env.py:314-335
+                if (__any_sync(FULL, M & startmask)) {                    // env.py:124-128
+                    R |= startmask;
+                    done = 1;
+                    outcome = 2;
+                } else {                                                  // env.py:129-133
+                    // Flood fill (env_numba.py:16-77) as a least fixed point: S grows by the
+                    // 8-neighbours of its zero-count cells that are not revealed / flagged /
+                    // mines; only the newest zero cells (the frontier) need dilating.
+                    const uint32_t zero = ~(pl.c0 | pl.c1 | pl.c2 | pl.c3) & g.valid;
+                    const uint32_t blocked = R | F | M;
+                    uint32_t S = startmask & ~F;                          // env.py:200 guard
+                    uint32_t front = S & zero;
+                    while (__any_sync(FULL, front)) {
+                        const uint32_t D = dilate8<CW>(front, lane, W, g) & ~blocked & ~S;
+                        S |= D;
+                        front = D & zero;
+                    }
+                    newly = warp_popc_sum(S);
+                    R |= S;
+                    reveal_branch = true;
+                }
+            } else if (first) {
+                pl = count_planes<CW>(M, lane, W, g);                     // no-op click, env.py:138-140
+            }
+            const int total = warp_popc_sum(R);
+            if (reveal_branch && total >= HW - p.mine_count) {            // env.py:134-137
+                done = 1;
+                outcome = 1;
+            }
+            const int step_now = meta.y + 1;                              // env.py:143
+
+            if (lane == 0) {                                              // env.py:493-505
+                p.reward[b] = done ? (outcome == 1 ? p.r_win : p.r_loss) : p.r_step;
+                p.done[b] = (uint8_t)done;
+                if (p.outcome) p.outcome[b] = (int8_t)outcome;
+                if (p.new_reveals) p.new_reveals[b] = newly;
+                if (p.step) p.step[b] = step_now;
+                if (p.rcount) p.rcount[b] = total;
+            }
+            if (done) {                                                   // auto-reset, env.py:497-498
+                M = 0u; R = 0u; F = 0u;
+                first = 0;
+                pl.c0 = pl.c1 = pl.c2 = pl.c3 = 0u;
+                if (own && p.flags) p.flags[b * wpb + lane] = 0u;
+                if (lane == 0) p.meta[b] = make_int4(0, 0, meta.z + 1, 0);
+            } else if (lane == 0) {
+                p.meta[b] = make_int4(first, step_now, meta.z, newly);
+            }
+            if (own) {
+                p.revealed[b * wpb + lane] = R;
+                if (mines_dirty || done) p.mines[b * wpb + lane] = M;
+            }
+        }
+        encode_board<CW, CHW>(p, b, lane, R, M, F, first, pl, g);
+    }
+}
+
+// Expansion of the bitboards into the reference's per-cell arrays for the
+// vec.envs[i] views (env.py:68-71, adjacent_counts per env.py:314-335).
+struct UnpackParams {
+    EnvParams e;
+    uint8_t *o_mine, *o_rev, *o_flags, *o_counts;
+};
+
+__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ UnpackParams q)
+{
+    const EnvParams &p = q.e;
+    const int lane = threadIdx.x & 31;
+    const int HW = p.HW, wpb = p.wpb;
+    const long long warps_per_block = blockDim.x >> 5;
+    const long long total_warps = (long long)gridDim.x * warps_per_block;
+    Geo g;
+    g.valid = p.g_valid[lane];
+    g.notcol0 = p.g_notcol0[lane];
+    g.notlast = p.g_notlast[lane];
+    for (long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < p.n; b += total_warps) {
+        uint32_t M = 0, R = 0, F = 0;
+        if (lane < wpb) {
+            M = p.mines[b * wpb + lane];
+            R = p.revealed[b * wpb + lane];
+            if (p.flags) F = p.flags[b * wpb + lane];
+        }
+        const Planes pl = count_planes<0>(M, lane, p.W, g);
+        for (int it = 0; it < wpb; ++it) {
+            const int cell = it * 32 + lane;
+            const uint32_t m = (__shfl_sync(FULL, M, it) >> lane) & 1u;
+            const uint32_t r = (__shfl_sync(FULL, R, it) >> lane) & 1u;
+            const uint32_t f = (__shfl_sync(FULL, F, it) >> lane) & 1u;
+            const uint32_t cnt = ((__shfl_sync(FULL, pl.c0, it) >> lane) & 1u) |
+                                 (((__shfl_sync(FULL, pl.c1, it) >> lane) & 1u) << 1) |
+                                 (((__shfl_sync(FULL, pl.c2, it) >> lane) & 1u) << 2) |
+                                 (((__shfl_sync(FULL, pl.c3, it) >> lane) & 1u) << 3);
+            if (cell >= HW) continue;
+            const long long o = b * (long long)HW + cell;
+            if (q.o_mine) q.o_mine[o] = (uint8_t)m;
+            if (q.o_rev) q.o_rev[o] = (uint8_t)r;
+            if (q.o_flags) q.o_flags[o] = (uint8_t)f;
+            if (q.o_counts) q.o_counts[o] = (uint8_t)cnt;
+        }
+    }
+}
+
+// Synthetic action source: one thread per env.
+struct ActParams {
+    const uint32_t *revealed;
+    int HW, wpb;
+    long long n, env_id_base;
+    uint32_t k0, k1, step_index;
+    int valid_only;
+    int32_t *a32;
+    long long *a64;
+};
+
+__device__ __forceinline__ uint32_t bounded(const uint32_t (&w)[4], uint32_t range)
+{
+    // Lemire's multiply-shift with rejection over the four words of one Philox block.
+    const uint32_t thresh = (0u - range) % range;
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned long long m = (unsigned long long)w[i] * range;
+        r = (uint32_t)(m >> 32);
+        if ((uint32_t)m >= thresh) break;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) random_actions_kernel(const ActParams p)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n) return;
+    const unsigned long long id = (unsigned long long)(p.env_id_base + b);
+    uint32_t w[4];
+    philox4x32_10(p.k0, p.k1 ^ 0x41435431u, (uint32_t)id, (uint32_t)(id >> 32), p.step_index, 0x5eedac71u, w);
+    int action = 0;
+    if (!p.valid_only) {
+        action = (int)bounded(w, (uint32_t)p.HW);
+    } else {
+        const uint32_t *R = p.revealed + b * p.wpb;
+        int cnt = 0;
+        for (int i = 0; i < p.wpb; ++i) {
+            uint32_t valid = (i == p.wpb - 1 && (p.HW & 31)) ? ((1u << (p.HW & 31)) - 1u) : 0xffffffffu;
+            cnt += __popc(~R[i] & valid);
+        }
+        if (cnt > 0) {
+            int k = (int)bounded(w, (uint32_t)cnt);
+            for (int i = 0; i < p.wpb; ++i) {
+                uint32_t valid = (i == p.wpb - 1 && (p.HW & 31)) ? ((1u << (p.HW & 31)) - 1u) : 0xffffffffu;
+                const uint32_t free_cells = ~R[i] & valid;
+                const int c = __popc(free_cells);
+                if (k < c) {
+                    action = i * 32 + (int)__fns(free_cells, 0, k + 1);
+                    break;
+                }
+                k -= c;
+            }
+        }
+    }
+    if (p.a32) p.a32[b] = action;
+    if (p.a64) p.a64[b] = action;
+}
+
+// ---------------------------------------------------------------------------
+// Host side of the C ABI
+// ---------------------------------------------------------------------------
+static int fill_params(EnvParams &p, const msw_env_desc *d, const msw_state *st, long long n)
+{
+    if (!d || !st) return fail(MSW_ERR_NULL, "desc/state is NULL");
+    if (d->H < 1 || d->W < 1 || d->W > 32 || (long long)d->H * d->W > MSW_MAX_CELLS)
+        return fail(MSW_ERR_BAD_SHAPE, "board %dx%d unsupported (need 1<=W<=32, H*W<=%d)", d->H, d->W, MSW_MAX_CELLS);
+    if (d->mine_count < 0 || d->mine_count > d->H * d->W - 1)
+        return fail(MSW_ERR_BAD_SHAPE, "mine_count %d out of range for %dx%d", d->mine_count, d->H, d->W);
+    if (n < 0) return fail(MSW_ERR_BAD_SHAPE, "n=%lld < 0", n);
+    if (!st->mines || !st->revealed || !st->meta) return fail(MSW_ERR_NULL, "state pointer is NULL");
+    if (((uintptr_t)st->meta & 15u) != 0) return fail(MSW_ERR_ALIGN, "state.meta must be 16-byte aligned");
+    memset(&p, 0, sizeof(p));
+    p.H = d->H; p.W = d->W; p.HW = d->H * d->W; p.wpb = (p.HW + 31) / 32;
+    p.mine_count = d->mine_count; p.safe = d->safe_nbhd != 0;
+    p.r_step = d->reward_step; p.r_loss = d->reward_loss; p.r_win = d->reward_win;
+    p.k0 = (uint32_t)d->seed; p.k1 = (uint32_t)(d->seed >> 32);
+    p.thresh16 = 65536u % (uint32_t)p.HW;
+    p.env_id_base = d->env_id_base;
+    p.n = n;
+    p.mines = st->mines; p.revealed = st->revealed; p.flags = st->flags;
+    p.meta = reinterpret_cast<int4 *>(st->meta);
+    for (int w = 0; w < 32; ++w) {
+        uint32_t v = 0, a = 0, z = 0;
+        for (int j = 0; j < 32; ++j) {
+            const int cell = w * 32 + j;
+            if (cell >= p.HW) break;
+            const int col = cell % p.W;
+            v |= 1u << j;
+            if (col != 0) a |= 1u << j;
+            if (col != p.W - 1) z |= 1u << j;
+        }
+        p.g_valid[w] = v; p.g_notcol0[w] = a; p.g_notlast[w] = z;
+    }
+    return MSW_OK;
+}
+
+static int set_encode_out(EnvParams &p, const msw_encode_out *out, bool require)
+{
+    if (!out) return require ? fail(MSW_ERR_NULL, "encode outputs are NULL") : MSW_OK;
+    p.obs = out->obs; p.mask = out->mask; p.labels = out->mine_labels; p.valid = out->mine_valid;
+    if ((p.HW & 3) == 0) {
+        if (((uintptr_t)p.obs & 15u) || ((uintptr_t)p.labels & 15u) || ((uintptr_t)p.mask & 3u) ||
+            ((uintptr_t)p.valid & 3u))
+            return fail(MSW_ERR_ALIGN, "obs/mine_labels must be 16-byte and mask/mine_valid 4-byte aligned");
+    }
+    return MSW_OK;
+}
+
+static inline int grid_for(long long n)
+{
+    const long long blocks = (n + 7) / 8;                     // 8 warps (boards) per 256-thread CTA
+    const long long cap = (long long)sm_count() * 8;          // persistent: <= 8 CTAs per SM, grid-stride
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <int MODE>
+static int launch_env(const EnvParams &p, cudaStream_t s)
+{
+    if (p.n == 0) return MSW_OK;
+    const int grid = grid_for(p.n);
+    if (p.W == 16 && p.HW == 256)
+        env_kernel<MODE, 16, 256><<<grid, 256, 0, s>>>(p);
+    else
+        env_kernel<MODE, 0, 0><<<grid, 256, 0, s>>>(p);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+}  // namespace msw
+
+using namespace msw;
+
+extern "C" int msw_reset(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                         const msw_encode_out *out, void *stream)
+{
+    EnvParams p;
+    int rc = fill_params(p, desc, st, n);
+    if (rc) return rc;
+    if ((rc = set_encode_out(p, out, false))) return rc;
+    return launch_env<MODE_RESET>(p, (cudaStream_t)stream);
+}
+
+extern "C" int msw_encode(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                          const msw_encode_out *out, void *stream)
+{
+    EnvParams p;
+    int rc = fill_params(p, desc, st, n);
+    if (rc) return rc;
+    if ((rc = set_encode_out(p, out, true))) return rc;
+    return launch_env<MODE_ENCODE>(p, (cudaStream_t)stream);
+}
+
+static int fill_step(EnvParams &p, const msw_env_desc *desc, const msw_state *st, const msw_step_io *io, int64_t n)
+{
+    int rc = fill_params(p, desc, st, n);
+    if (rc) return rc;
+    if (!io) return fail(MSW_ERR_NULL, "io is NULL");
+    if ((io->actions32 != nullptr) == (io->actions64 != nullptr))
+        return fail(MSW_ERR_ARG, "exactly one of actions32/actions64 must be set");
+    if (!io->reward || !io->done) return fail(MSW_ERR_NULL, "reward/done outputs are required");
+    if ((io->inject_sel != nullptr) != (io->inject_bits != nullptr))
+        return fail(MSW_ERR_ARG, "inject_bits and inject_sel must be given together");
+    p.a32 = io->actions32;
+    p.a64 = reinterpret_cast<const long long *>(io->actions64);
+    p.inj_bits = io->inject_bits; p.inj_sel = io->inject_sel;
+    p.reward = io->reward; p.done = io->done; p.outcome = io->outcome;
+    p.new_reveals = io->new_reveals; p.step = io->step; p.rcount = io->revealed_count;
+    return set_encode_out(p, &io->enc, false);
+}
+
+extern "C" int msw_step(const msw_env_desc *desc, const msw_state *st, const msw_step_io *io,
+                        int64_t n, void *stream)
+{
+    EnvParams p;
+    int rc = fill_step(p, desc, st, io, n);
+    if (rc) return rc;
+    return launch_env<MODE_STEP>(p, (cudaStream_t)stream);
+}
+
+extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, const msw_step_io *io,
+                             const int32_t *h_actions32, const msw_host_out *h, int64_t n, void *stream)
+{
+    EnvParams p;
+    int rc = fill_step(p, desc, st, io, n);
+    if (rc) return rc;
+    if (!h_actions32 || !io->actions32) return fail(MSW_ERR_NULL, "msw_step_host needs h_actions32 and io->actions32 staging");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)n, HW = (size_t)p.HW;
+    MSW_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(io->actions32), h_actions32, N * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_env<MODE_STEP>(p, s))) return rc;
+    if (h) {
+#define MSW_D2H(dst, src, bytes)                                                              \
+    if (dst) {                                                                                \
+        if (!(src)) return fail(MSW_ERR_NULL, "host output " #dst " requested without device staging"); \
+        MSW_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));            \
+    }
+        MSW_D2H(h->obs, p.obs, N * MSW_OBS_CHANNELS * HW * 4)
+        MSW_D2H(h->mask, p.mask, N * HW)
+        MSW_D2H(h->reward, p.reward, N * 4)
+        MSW_D2H(h->done, p.done, N)
+        MSW_D2H(h->outcome, p.outcome, N)
+        MSW_D2H(h->new_reveals, p.new_reveals, N * 4)
+        MSW_D2H(h->step, p.step, N * 4)
+        MSW_D2H(h->revealed_count, p.rcount, N * 4)
+#undef MSW_D2H
+    }
+    MSW_CUDA_TRY(cudaStreamSynchronize(s));
+    return MSW_OK;
+}
+
+extern "C" int msw_unpack_state(const msw_env_desc *desc, const msw_state *st, int64_t n, uint8_t *mine,
+                                uint8_t *revealed, uint8_t *flags, uint8_t *counts, void *stream)
+{
+    UnpackParams q;
+    int rc = fill_params(q.e, desc, st, n);
+    if (rc) return rc;
+    q.o_mine = mine; q.o_rev = revealed; q.o_flags = flags; q.o_counts = counts;
+    if (n == 0) return MSW_OK;
+    unpack_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(q);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+extern "C" int msw_random_actions(const msw_env_desc *desc, const msw_state *st, int64_t n, uint64_t seed,
+                                  uint32_t step_index, int32_t valid_only, int32_t *a32, int64_t *a64,
+                                  void *stream)
+{
+    EnvParams e;
+    int rc = fill_params(e, desc, st, n);
+    if (rc) return rc;
+    if (!a32 && !a64) return fail(MSW_ERR_NULL, "no action output given");
+    if (n == 0) return MSW_OK;
+    ActParams p;
+    p.revealed = st->revealed; p.HW = e.HW; p.wpb = e.wpb; p.n = n; p.env_id_base = desc->env_id_base;
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.step_index = step_index;
+    p.valid_only = valid_only; p.a32 = a32; p.a64 = reinterpret_cast<long long *>(a64);
+    random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}

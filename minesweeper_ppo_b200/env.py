@@ -1,0 +1,465 @@
+"""Device-resident vectorised Minesweeper environment with the reference's API.
+
+Mirrors `minesweeper/env.py` of yakvrz/minesweeper-ppo for the rollout hot path:
+
+    EnvConfig                      env.py:19-30
+    VecMinesweeper(num_envs, cfg, seed=0, late_start_cfg=None, late_start_seed=None)
+                                   env.py:382-403
+      .reset() -> {"obs","action_mask"}                         env.py:468-477
+      .step(actions) -> (batch, rewards, dones, infos)          env.py:479-511
+      .envs[i].{revealed,flags,mine_mask,adjacent_counts,first_click_done,step_count,H,W,cfg}
+                                   env.py:68-75 (read-only views, unpacked lazily)
+      .num_envs, .cfg, .action_space(), .obs_channels()         env.py:391-392, 513-517
+
+All state lives in HBM as bitboards and every call is one CUDA launch through the
+C ABI of include/msw_b200.h.  Two calling conventions, chosen at construction:
+
+  api="numpy"  (default -- what the reference's callers expect): NumPy in, NumPy
+               out, list-of-dict `infos`; each call copies through pinned host
+               memory (msw_step_host).
+  api="torch"  native: CUDA tensors in and out, tensor-valued infos, optional
+               `out=` buffers so the kernel writes straight into a rollout buffer.
+
+There is no CPU implementation in this package: without the CUDA library / a CUDA
+device the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+OBS_CHANNELS = _lib.OBS_CHANNELS
+_OUTCOME_NAMES = (None, "win", "loss")
+
+
+@dataclass
+class EnvConfig:
+    """Same fields and defaults as the reference EnvConfig (env.py:19-30)."""
+    H: int = 8
+    W: int = 8
+    mine_count: int = 10
+    guarantee_safe_neighborhood: bool = True
+    use_pair_constraints: Optional[bool] = None  # deprecated in the reference, unused
+    solver_preset: str = "zf"
+
+    win_reward: float = 1.0
+    loss_reward: float = -1.0
+    step_penalty: float = 1e-4
+
+
+def reward_constants(cfg) -> Tuple[np.float32, np.float32, np.float32]:
+    """(step, loss, win) rewards rounded exactly as the reference does: accumulated in
+    Python float64 (env.py:110,128,137,142) and stored into a float32 array (env.py:501)."""
+    pen = float(cfg.step_penalty)
+    step = np.float32(0.0 - pen)
+    loss = np.float32((0.0 + float(cfg.loss_reward)) - pen)
+    win = np.float32((0.0 + float(cfg.win_reward)) - pen)
+    return step, loss, win
+
+
+def pack_boards(cells: np.ndarray, HW: int) -> np.ndarray:
+    """bool [n, HW] (or [n,H,W]) -> int32 [n, wpb] flat little-endian bitboards."""
+    cells = np.asarray(cells).reshape(-1, HW).astype(np.uint8)
+    wpb = (HW + 31) // 32
+    packed = np.packbits(cells, axis=1, bitorder="little")
+    out = np.zeros((cells.shape[0], wpb * 4), np.uint8)
+    out[:, : packed.shape[1]] = packed
+    return out.view("<u4").view(np.int32).reshape(cells.shape[0], wpb)
+
+
+@dataclass
+class StepOut:
+    """Caller-owned destination tensors for `step(..., out=)` / `reset(out=)` (CUDA,
+    contiguous).  Any of the optional members may be None."""
+    obs: torch.Tensor                       # f32 [n,10,H,W]
+    action_mask: torch.Tensor               # bool [n,HW]
+    rewards: Optional[torch.Tensor] = None  # f32 [n]
+    dones: Optional[torch.Tensor] = None    # bool [n]
+    mine_labels: Optional[torch.Tensor] = None   # f32 [n,H,W]
+    mine_valid: Optional[torch.Tensor] = None    # bool [n,H,W]
+
+
+class _EnvView:
+    """Read-only stand-in for `vec.envs[i]` (MinesweeperEnv attributes, env.py:41-75)."""
+
+    def __init__(self, vec: "VecMinesweeper", i: int):
+        self._vec, self._i = vec, i
+        self.cfg = vec.cfg
+        self.H, self.W = vec.H, vec.W
+        self.cell_count = self.reveal_count = self.A = vec.HW
+
+    def _cells(self, key: str) -> np.ndarray:
+        return self._vec._unpacked()[key][self._i].reshape(self.H, self.W)
+
+    @property
+    def mine_mask(self) -> np.ndarray: return self._cells("mine").view(bool)
+    @property
+    def revealed(self) -> np.ndarray: return self._cells("revealed").view(bool)
+    @property
+    def flags(self) -> np.ndarray: return self._cells("flags").view(bool)
+    @property
+    def adjacent_counts(self) -> np.ndarray: return self._cells("counts")
+    @property
+    def first_click_done(self) -> bool: return bool(self._vec._unpacked()["meta"][self._i, 0])
+    @property
+    def step_count(self) -> int: return int(self._vec._unpacked()["meta"][self._i, 1])
+    @property
+    def _last_new_reveals(self) -> int: return int(self._vec._unpacked()["meta"][self._i, 3])
+    @property
+    def action_space(self) -> int: return self.A                  # env.py:154-156 (property)
+    @property
+    def obs_channels(self) -> int: return OBS_CHANNELS            # env.py:158-160 (property)
+
+
+class _EnvList:
+    def __init__(self, vec: "VecMinesweeper"):
+        self._vec = vec
+
+    def __len__(self) -> int: return self._vec.num_envs
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return _EnvView(self._vec, i)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class VecMinesweeper:
+    """Batched Minesweeper on one B200; API of the reference class (env.py:379-517)."""
+
+    def __init__(
+        self,
+        num_envs: int,
+        cfg: EnvConfig,
+        seed: int = 0,
+        late_start_cfg: Optional[Dict[str, Any]] = None,
+        late_start_seed: Optional[int] = None,
+        *,
+        device: Union[str, torch.device, None] = None,
+        api: str = "numpy",
+        env_id_base: int = 0,
+        aux_maps: bool = False,
+    ):
+        assert num_envs > 0                                           # env.py:390
+        if api not in ("numpy", "torch"):
+            raise ValueError("api must be 'numpy' or 'torch'")
+        if late_start_cfg:
+            raise NotImplementedError(
+                "late_start_cfg (env.py:416-466) is not implemented on device yet (SURVEY 8f, row f3)")
+        self._L = _lib.load()                                         # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("VecMinesweeper needs a CUDA device; this package has no CPU fallback")
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self.api = api
+        self.aux_maps = bool(aux_maps)
+        self.seed = int(seed)
+        self.H, self.W = int(cfg.H), int(cfg.W)
+        self.HW = self.H * self.W
+        self.wpb = self._L.msw_words_per_board(self.H, self.W)
+        if self.wpb == 0:
+            raise ValueError(f"unsupported board {self.H}x{self.W}: need 1<=W<=32 and H*W<={_lib.MAX_CELLS}")
+        if not 0 <= int(cfg.mine_count) <= self.HW - 1:
+            raise ValueError(f"mine_count {cfg.mine_count} out of range for {self.H}x{self.W}")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("VecMinesweeper state lives in HBM; device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+        n, dev = self.num_envs, self.device
+        self._mines = torch.zeros((n, self.wpb), dtype=torch.int32, device=dev)
+        self._revealed = torch.zeros((n, self.wpb), dtype=torch.int32, device=dev)
+        self._flags: Optional[torch.Tensor] = None                    # allocated only if flags are ever set
+        self._meta = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+
+        rs, rl, rw = reward_constants(cfg)
+        self.reward_constants = (rs, rl, rw)
+        self._desc = _lib.EnvDesc(self.H, self.W, int(cfg.mine_count), int(bool(cfg.guarantee_safe_neighborhood)),
+                                  float(rs), float(rl), float(rw), 0, self.seed & 0xFFFFFFFFFFFFFFFF, int(env_id_base))
+        self._state = _lib.State()
+        self._sync_state_struct()
+        self._io = _lib.StepIO()
+        self._inject: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        self._cache: Optional[Dict[str, np.ndarray]] = None
+        self._pinned: Dict[str, torch.Tensor] = {}
+        self._staging: Dict[str, torch.Tensor] = {}
+        self.envs = _EnvList(self)
+        self.mine_labels: Optional[torch.Tensor] = None               # aux maps of the last reset/step
+        self.mine_valid: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ helpers
+    def _sync_state_struct(self) -> None:
+        s = self._state
+        s.mines, s.revealed, s.meta = self._mines.data_ptr(), self._revealed.data_ptr(), self._meta.data_ptr()
+        s.flags = self._flags.data_ptr() if self._flags is not None else None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, t: Optional[torch.Tensor], shape, dtype, name: str) -> Optional[int]:
+        if t is None:
+            return None
+        if t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError(f"{name}: need contiguous {dtype} {tuple(shape)} on {self.device}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device}")
+        return t.data_ptr()
+
+    def _alloc_encode(self) -> StepOut:
+        n, dev = self.num_envs, self.device
+        return StepOut(
+            obs=torch.empty((n, OBS_CHANNELS, self.H, self.W), dtype=torch.float32, device=dev),
+            action_mask=torch.empty((n, self.HW), dtype=torch.bool, device=dev),
+            mine_labels=torch.empty((n, self.H, self.W), dtype=torch.float32, device=dev) if self.aux_maps else None,
+            mine_valid=torch.empty((n, self.H, self.W), dtype=torch.bool, device=dev) if self.aux_maps else None,
+        )
+
+    def _fill_encode(self, enc: _lib.EncodeOut, o: StepOut) -> None:
+        n = self.num_envs
+        enc.obs = self._check(o.obs, (n, OBS_CHANNELS, self.H, self.W), torch.float32, "obs")
+        enc.mask = self._check(o.action_mask, (n, self.HW), torch.bool, "action_mask")
+        enc.mine_labels = self._check(o.mine_labels, (n, self.H, self.W), torch.float32, "mine_labels")
+        enc.mine_valid = self._check(o.mine_valid, (n, self.H, self.W), torch.bool, "mine_valid")
+
+    def action_space(self) -> int:                                    # env.py:513-514
+        return self.HW
+
+    def obs_channels(self) -> int:                                    # env.py:516-517
+        return OBS_CHANNELS
+
+    # ------------------------------------------------------------------ reset
+    def reset(self, out: Optional[StepOut] = None) -> Dict[str, Any]:
+        """VecMinesweeper.reset (env.py:468-477)."""
+        o = out if out is not None else self._alloc_encode()
+        enc = _lib.EncodeOut()
+        self._fill_encode(enc, o)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.msw_reset(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                         C.byref(enc), self._stream()), "msw_reset")
+        self._cache = None
+        self._inject = None
+        self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
+        if self.api == "numpy":
+            return {"obs": o.obs.cpu().numpy(), "action_mask": o.action_mask.cpu().numpy()}
+        return {"obs": o.obs, "action_mask": o.action_mask}
+
+    # ------------------------------------------------------------------ test / compat hooks
+    def inject_layouts(self, mine: Union[np.ndarray, torch.Tensor], sel: Union[np.ndarray, torch.Tensor]) -> None:
+        """Parity-harness hook: envs with sel[i] that place their mines during the
+        NEXT step take mine[i] (bool [n,HW] / [n,H,W]) instead of sampling."""
+        if isinstance(mine, torch.Tensor):
+            mine = mine.cpu().numpy()
+        if isinstance(sel, torch.Tensor):
+            sel = sel.cpu().numpy()
+        bits = torch.from_numpy(pack_boards(mine, self.HW)).to(self.device)
+        s = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.uint8)).to(self.device)
+        assert bits.shape == (self.num_envs, self.wpb) and s.shape == (self.num_envs,)
+        self._inject = (bits, s)
+
+    def set_state(self, *, mine=None, revealed=None, flags=None, first_click_done=None, step_count=None) -> None:
+        """Overwrite parts of the device state from per-cell host arrays (tests, late-start tooling)."""
+        n = self.num_envs
+        if mine is not None:
+            self._mines.copy_(torch.from_numpy(pack_boards(mine, self.HW)))
+        if revealed is not None:
+            self._revealed.copy_(torch.from_numpy(pack_boards(revealed, self.HW)))
+        if flags is not None:
+            if self._flags is None:
+                self._flags = torch.zeros((n, self.wpb), dtype=torch.int32, device=self.device)
+            self._flags.copy_(torch.from_numpy(pack_boards(flags, self.HW)))
+        if first_click_done is not None:
+            self._meta[:, 0] = torch.as_tensor(np.asarray(first_click_done, dtype=np.int32), device=self.device)
+        if step_count is not None:
+            self._meta[:, 1] = torch.as_tensor(np.asarray(step_count, dtype=np.int32), device=self.device)
+        self._sync_state_struct()
+        self._cache = None
+
+    def encode(self, out: Optional[StepOut] = None) -> Dict[str, Any]:
+        """Observation / mask (/aux maps) of the current state without stepping."""
+        o = out if out is not None else self._alloc_encode()
+        enc = _lib.EncodeOut()
+        self._fill_encode(enc, o)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.msw_encode(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                          C.byref(enc), self._stream()), "msw_encode")
+        self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
+        if self.api == "numpy":
+            return {"obs": o.obs.cpu().numpy(), "action_mask": o.action_mask.cpu().numpy()}
+        return {"obs": o.obs, "action_mask": o.action_mask}
+
+    def _unpacked(self) -> Dict[str, np.ndarray]:
+        """Lazy device->host expansion of the bitboards for the `.envs[i]` views."""
+        if self._cache is None:
+            n, HW, dev = self.num_envs, self.HW, self.device
+            bufs = [torch.empty((n, HW), dtype=torch.uint8, device=dev) for _ in range(4)]
+            with torch.cuda.device(dev):
+                _lib.check(self._L.msw_unpack_state(C.byref(self._desc), C.byref(self._state), n,
+                                                    *[b.data_ptr() for b in bufs], self._stream()),
+                           "msw_unpack_state")
+            names = ("mine", "revealed", "flags", "counts")
+            self._cache = {k: b.cpu().numpy() for k, b in zip(names, bufs)}
+            self._cache["meta"] = self._meta.cpu().numpy()
+        return self._cache
+
+    def random_actions(self, step_index: int, valid_only: bool = True, seed: int = 1,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Synthetic action source: uniformly random unrevealed cell
+        (or any cell) per env, generated on device."""
+        if out is None:
+            out = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        a32 = out.data_ptr() if out.dtype == torch.int32 else None
+        a64 = out.data_ptr() if out.dtype == torch.int64 else None
+        if (a32 is None and a64 is None) or out.device != self.device or out.shape != (self.num_envs,):
+            raise ValueError("random_actions: out must be int32/int64 [num_envs] on the env device")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.msw_random_actions(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index) & 0xFFFFFFFF,
+                                                  int(valid_only), a32, a64, self._stream()),
+                       "msw_random_actions")
+        return out
+
+    # ------------------------------------------------------------------ step
+    def _info_tensors(self) -> Dict[str, torch.Tensor]:
+        st = self._staging
+        if "outcome" not in st:
+            n, dev = self.num_envs, self.device
+            st["outcome"] = torch.empty((n,), dtype=torch.int8, device=dev)
+            st["new_reveals"] = torch.empty((n,), dtype=torch.int32, device=dev)
+            st["step"] = torch.empty((n,), dtype=torch.int32, device=dev)
+            st["revealed_count"] = torch.empty((n,), dtype=torch.int32, device=dev)
+        return st
+
+    def step(self, actions, out: Optional[StepOut] = None, want_infos: bool = True):
+        """VecMinesweeper.step (env.py:479-511).  Returns (batch, rewards, dones, infos)."""
+        if self.api == "numpy":
+            return self._step_numpy(actions)
+        n, dev = self.num_envs, self.device
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        assert tuple(actions.shape) == (n,)                           # env.py:480
+        if actions.dtype not in (torch.int32, torch.int64):
+            actions = actions.to(torch.int64)
+        actions = actions.to(dev).contiguous()
+        o = out if out is not None else self._alloc_encode()
+        rewards = o.rewards if o.rewards is not None else torch.empty((n,), dtype=torch.float32, device=dev)
+        dones = o.dones if o.dones is not None else torch.empty((n,), dtype=torch.bool, device=dev)
+        io = self._io
+        io.actions32 = actions.data_ptr() if actions.dtype == torch.int32 else None
+        io.actions64 = actions.data_ptr() if actions.dtype == torch.int64 else None
+        io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
+                                         if self._inject is not None else (None, None))
+        io.reward = self._check(rewards, (n,), torch.float32, "rewards")
+        io.done = self._check(dones, (n,), torch.bool, "dones")
+        infos: Dict[str, Any] = {}
+        if want_infos:
+            it = self._info_tensors()
+            io.outcome, io.new_reveals = it["outcome"].data_ptr(), it["new_reveals"].data_ptr()
+            io.step, io.revealed_count = it["step"].data_ptr(), it["revealed_count"].data_ptr()
+            infos = {"outcome_code": it["outcome"], "last_new_reveals": it["new_reveals"], "step": it["step"],
+                     "revealed_count": it["revealed_count"], "done": dones}
+        else:
+            io.outcome = io.new_reveals = io.step = io.revealed_count = None
+        self._fill_encode(io.enc, o)
+        with torch.cuda.device(dev):
+            _lib.check(self._L.msw_step(C.byref(self._desc), C.byref(self._state), C.byref(io), n, self._stream()),
+                       "msw_step")
+        self._inject = None
+        self._cache = None
+        self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
+        return {"obs": o.obs, "action_mask": o.action_mask}, rewards, dones, infos
+
+    # reference calling convention: NumPy in / NumPy out through pinned host buffers
+    def _host_buffers(self) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
+        if not self._pinned:
+            n, H, W, HW, dev = self.num_envs, self.H, self.W, self.HW, self.device
+            spec = {
+                "actions": ((n,), torch.int32), "obs": ((n, OBS_CHANNELS, H, W), torch.float32),
+                "mask": ((n, HW), torch.bool), "reward": ((n,), torch.float32), "done": ((n,), torch.bool),
+                "outcome": ((n,), torch.int8), "new_reveals": ((n,), torch.int32), "step": ((n,), torch.int32),
+                "revealed_count": ((n,), torch.int32),
+            }
+            for k, (shape, dt) in spec.items():
+                self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
+                self._staging["h_" + k] = torch.empty(shape, dtype=dt, device=dev)
+            if self.aux_maps:
+                self._staging["h_labels"] = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+                self._staging["h_valid"] = torch.empty((n, H, W), dtype=torch.bool, device=dev)
+        return self._pinned, self._staging
+
+    def step_host(self, actions_pinned: torch.Tensor, *, copy_obs: bool = True, copy_infos: bool = True
+                  ) -> Dict[str, torch.Tensor]:
+        """msw_step_host: pinned int32 actions in; pinned outputs back (obs/mask optional);
+        synchronises the current stream.  Returns the pinned tensors (valid until the next call)."""
+        n = self.num_envs
+        pin, st = self._host_buffers()
+        if not (actions_pinned.dtype == torch.int32 and actions_pinned.is_pinned() and
+                tuple(actions_pinned.shape) == (n,) and actions_pinned.is_contiguous()):
+            raise ValueError("step_host: actions must be a pinned contiguous int32 [num_envs] CPU tensor")
+        io = self._io
+        io.actions32, io.actions64 = st["h_actions"].data_ptr(), None
+        io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
+                                         if self._inject is not None else (None, None))
+        io.reward, io.done = st["h_reward"].data_ptr(), st["h_done"].data_ptr()
+        io.outcome, io.new_reveals = st["h_outcome"].data_ptr(), st["h_new_reveals"].data_ptr()
+        io.step, io.revealed_count = st["h_step"].data_ptr(), st["h_revealed_count"].data_ptr()
+        io.enc.obs, io.enc.mask = st["h_obs"].data_ptr(), st["h_mask"].data_ptr()
+        io.enc.mine_labels = st["h_labels"].data_ptr() if self.aux_maps else None
+        io.enc.mine_valid = st["h_valid"].data_ptr() if self.aux_maps else None
+        h = _lib.HostOut()
+        h.reward, h.done = pin["reward"].data_ptr(), pin["done"].data_ptr()
+        if copy_obs:
+            h.obs, h.mask = pin["obs"].data_ptr(), pin["mask"].data_ptr()
+        if copy_infos:
+            h.outcome, h.new_reveals = pin["outcome"].data_ptr(), pin["new_reveals"].data_ptr()
+            h.step, h.revealed_count = pin["step"].data_ptr(), pin["revealed_count"].data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.msw_step_host(C.byref(self._desc), C.byref(self._state), C.byref(io),
+                                             actions_pinned.data_ptr(), C.byref(h), n, self._stream()),
+                       "msw_step_host")
+        self._inject = None
+        self._cache = None
+        if self.aux_maps:
+            self.mine_labels, self.mine_valid = st["h_labels"], st["h_valid"]
+        return pin
+
+    def _step_numpy(self, actions) -> Tuple[Dict[str, np.ndarray], np.ndarray, np.ndarray, Dict[str, Any]]:
+        n = self.num_envs
+        actions = np.asarray(actions)
+        assert actions.shape == (n,)                                  # env.py:480
+        pin, _ = self._host_buffers()
+        a = actions.astype(np.int64, copy=False)
+        # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32
+        if a.size and (a.max() > 2**31 - 1 or a.min() < -2**31):
+            a = np.mod(a, self.HW)
+        pin["actions"].numpy()[:] = a
+        self.step_host(pin["actions"])
+        rewards = pin["reward"].numpy().copy()
+        dones = pin["done"].numpy().copy()
+        outcome, newr = pin["outcome"].numpy(), pin["new_reveals"].numpy()
+        step, rc = pin["step"].numpy(), pin["revealed_count"].numpy()
+        infos = {                                                     # env.py:485-505
+            "aux": [{"step": int(step[i]), "last_new_reveals": int(newr[i]),
+                     "revealed_frac": float(int(rc[i]) / max(1, self.HW))} for i in range(n)],
+            "outcome": [_OUTCOME_NAMES[int(outcome[i])] for i in range(n)],
+            "done": [bool(dones[i]) for i in range(n)],
+        }
+        batch = {"obs": pin["obs"].numpy().copy(), "action_mask": pin["mask"].numpy().copy()}
+        return batch, rewards, dones, infos
+
+    # ------------------------------------------------------------------ raw state (native API)
+    @property
+    def state_tensors(self) -> Dict[str, Optional[torch.Tensor]]:
+        """Bitboard state in HBM: int32 [n, wpb] boards and int32 [n,4] meta."""
+        return {"mines": self._mines, "revealed": self._revealed, "flags": self._flags, "meta": self._meta}

@@ -179,7 +179,7 @@ class OracleVecEnv:
     """CPU oracle with the reference VecMinesweeper call shape (env.py:379-517)."""
 
     def __init__(self, num_envs: int, cfg, seed: int = 0, env_id_base: int = 0,
-                 nthreads: int = 1, aux_maps: bool = False):
+                 nthreads: int = 1, aux_maps: bool = False, reuse_out: bool = False):
         assert num_envs > 0                                   # env.py:390
         self.cfg, self.num_envs, self.seed = cfg, int(num_envs), int(seed)
         self.H, self.W = int(cfg.H), int(cfg.W)
@@ -200,17 +200,21 @@ class OracleVecEnv:
         self._ccfg = _ccfg(cfg, seed)
         self.envs = [_EnvView(self, i) for i in range(n)] if n <= 4096 else None
         self.mine_labels = self.mine_valid = None
+        self.reuse_out, self._out = bool(reuse_out), None   # reuse_out: outputs are overwritten each call
 
     def action_space(self) -> int: return self.HW           # env.py:513-514
     def obs_channels(self) -> int: return OBS_CHANNELS      # env.py:516-517
 
     def _alloc_out(self):
+        if self.reuse_out and self._out is not None:
+            return self._out
         n, H, W = self.num_envs, self.H, self.W
         obs = np.empty((n, OBS_CHANNELS, H, W), np.float32)
         mask = np.empty((n, self.HW), np.uint8)
         lab = np.empty((n, H, W), np.float32) if self.aux_maps else None
         val = np.empty((n, H, W), np.uint8) if self.aux_maps else None
-        return obs, mask, lab, val
+        self._out = (obs, mask, lab, val)
+        return self._out
 
     def reset(self) -> Dict[str, np.ndarray]:
         obs, mask, lab, val = self._alloc_out()

@@ -113,3 +113,36 @@ class OracleAdapter:
         v = self.v
         return dict(revealed=v.revealed.astype(bool), mine=v.mine.astype(bool), counts=v.counts.copy(),
                     first=v.first_click_done.astype(bool), step_count=v.step_count.copy())
+
+
+class CudaAdapter:
+    """The product path: minesweeper_ppo_b200.VecMinesweeper through the C ABI (native torch API)."""
+
+    def __init__(self, cfg, N, seed=0, env_id_base=0):
+        import torch
+        import minesweeper_ppo_b200 as m
+        self.torch = torch
+        ec = m.EnvConfig(H=cfg.H, W=cfg.W, mine_count=cfg.mine_count,
+                         guarantee_safe_neighborhood=cfg.guarantee_safe_neighborhood,
+                         win_reward=cfg.win_reward, loss_reward=cfg.loss_reward, step_penalty=cfg.step_penalty)
+        self.v = m.VecMinesweeper(N, ec, seed=seed, api="torch", aux_maps=True, env_id_base=env_id_base)
+
+    def reset(self):
+        b = self.v.reset()
+        return b["obs"].cpu().numpy(), b["action_mask"].cpu().numpy()
+
+    def step(self, actions, mine=None, sel=None):
+        if sel is not None:
+            self.v.inject_layouts(mine, sel)
+        a = actions if isinstance(actions, self.torch.Tensor) else self.torch.from_numpy(np.ascontiguousarray(actions))
+        b, r, d, info = self.v.step(a)
+        c = lambda t: t.cpu().numpy()
+        return dict(obs=c(b["obs"]), mask=c(b["action_mask"]), rewards=c(r), dones=c(d),
+                    outcome=c(info["outcome_code"]), new_reveals=c(info["last_new_reveals"]),
+                    step=c(info["step"]), revealed_count=c(info["revealed_count"]),
+                    labels=c(self.v.mine_labels), valid=c(self.v.mine_valid))
+
+    def state(self):
+        u = self.v._unpacked()
+        return dict(revealed=u["revealed"].astype(bool), mine=u["mine"].astype(bool), counts=u["counts"].copy(),
+                    first=u["meta"][:, 0].astype(bool), step_count=u["meta"][:, 1].copy())
