@@ -195,7 +195,8 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
                        action_mask=torch.empty((N, H * W), dtype=torch.bool, device=dev),
                        rewards=torch.empty((N,), dtype=torch.float32, device=dev),
                        dones=torch.empty((N,), dtype=torch.bool, device=dev)) for _ in range(ring)]
-    actions_log = torch.empty((Wm + K, N), dtype=torch.int32, device=dev)
+    Ke = min(K, 400)                           # steps replayed by the e2e legs
+    actions_log = torch.empty((Wm + Ke + 1, N), dtype=torch.int32, device=dev)
     vec.reset(out=slots[0])
     for t in range(Wm):
         vec.random_actions(t, out=actions_log[t])
@@ -208,7 +209,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     sampler.start()
     ev0.record()
     for t in range(K):
-        a = actions_log[Wm + t]
+        a = actions_log[Wm + min(t, Ke)]       # first Ke action sets are kept for the e2e replay
         vec.random_actions(Wm + t, out=a)
         kev[t][0].record()
         vec.step(a, out=slots[t % ring], want_infos=False)
@@ -223,7 +224,6 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     # -- e2e: same workload through the host-buffer C-ABI call (msw_step_host): per step, this
     # step's actions come from pinned host memory (H2D) and rewards+dones go back to pinned host
     # memory (D2H); obs/mask land in device memory where the policy consumes them.
-    Ke = min(K, 400)
     acts_host = actions_log[: Wm + Ke].cpu().pin_memory()
     del actions_log
 
@@ -307,9 +307,8 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         rate, _, _ = cpu_env_steps_per_s(4096, 3, 1, threads)
-        steps_c = 8
-        n_c = int(max(1024, min(ENVS_PER_GPU, rate * 15.0 / steps_c)))
-        n_c = 1 << (n_c.bit_length() - 1)
+        n_c = ENVS_PER_GPU
+        steps_c = int(max(8, min(4000, rate * 12.0 / n_c)))      # about 10-15 s of CPU work
         v_c, total_c, _ = cpu_env_steps_per_s(n_c, steps_c, 2, threads)
         line["cpu_baseline"] = {
             "value": v_c, "unit": UNIT, "cores": threads, "kind": "port",
@@ -323,7 +322,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
