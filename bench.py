@@ -245,9 +245,13 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         wall = time.perf_counter() - t0
         return max(e0.elapsed_time(e1) / 1e3, 0.0), wall, done_count
 
-    e2e_s, e2e_wall, episodes = run_host(False, Ke)
-    Kh = min(Ke, 12)
-    e2e_full_s, _, _ = run_host(True, Kh)
+    if args.no_e2e:
+        Kh = 1
+        e2e_s, e2e_full_s, episodes = float("inf"), float("inf"), None
+    else:
+        e2e_s, e2e_wall, episodes = run_host(False, Ke)
+        Kh = min(Ke, 12)
+        e2e_full_s, _, _ = run_host(True, Kh)
 
     def reduce_max(x: float) -> float:
         if world == 1:
@@ -327,6 +331,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value and roofline only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -16,6 +16,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace msw {
@@ -55,12 +56,20 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
 // ---------------------------------------------------------------------------
 // First-click-safe placement (replaces env.py:280-312).  Forbidden set and the
 // tiny-board fallback follow the reference; the subset itself is drawn with the
-// counter-based sampler of DESIGN.md (NumPy's PCG64 stream is outside the
-// parity contract): 16-bit Lemire draws over all cells in Philox stream order,
-// rejecting forbidden / already chosen cells -- exactly uniform over
-// mine_count-subsets of the allowed cells.  All lanes walk the same draw
-// sequence; lane l generates Philox block (32*batch + l), so one Philox call per
-// lane yields 256 draws for the warp.
+// counter-based sampler specified in DESIGN.md (NumPy's PCG64 stream is outside
+// the parity contract).  Specification: a stream of 16-bit draws p = 0,1,2,...;
+// draw p is 16-bit slot (p%256)/32 of Philox block 32*(p/256) + p%32 keyed by
+// (seed; env id, episode); each draw proposes cell floor(x*HW/2^16) (Lemire,
+// rejected when (x*HW mod 2^16) < 2^16 mod HW) and is accepted iff the cell is
+// neither forbidden nor already chosen; stop at mine_count accepted cells
+// (complement when more than half of the allowed cells are mines).  Sequential
+// rejection sampling without replacement is exactly uniform over subsets.
+//
+// Evaluation is warp-parallel and order-exact: lane l owns Philox block
+// 32*batch + l, so one round tests 32 consecutive draws at once; a draw is
+// "novel" if its cell is free and no lower lane proposes the same cell
+// (match.any), and only the first (K - accepted) novel draws are kept (ballot +
+// lane-mask popcount), which is exactly what the sequential walk would do.
 // ---------------------------------------------------------------------------
 template <int CW, int CHW>
 __device__ __noinline__ uint32_t sample_mines(const EnvParams &p, long long env_id, uint32_t episode,
@@ -68,6 +77,7 @@ __device__ __noinline__ uint32_t sample_mines(const EnvParams &p, long long env_
 {
     const int W = CW ? CW : p.W;
     const int HW = CHW ? CHW : p.HW;
+    const int wpb = (HW + 31) >> 5;
     const int M = p.mine_count;
     uint32_t forb = startmask;
     if (p.safe) forb |= dilate8<CW>(startmask, lane, W, g);          // env.py:288-299
@@ -78,29 +88,36 @@ __device__ __noinline__ uint32_t sample_mines(const EnvParams &p, long long env_
     }
     const bool comp = 2 * M > allowed;          // sample the complement when dense
     const int K = comp ? allowed - M : M;
-    const uint32_t thresh = p.thresh16;
+    const uint32_t thresh = CHW ? (65536u % (uint32_t)(CHW ? CHW : 1)) : p.thresh16;
     const uint32_t id_lo = (uint32_t)(unsigned long long)env_id;
     const uint32_t id_hi = (uint32_t)((unsigned long long)env_id >> 32);
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     uint32_t chosen = 0;
     int cnt = 0;
     for (uint32_t batch = 0; cnt < K; ++batch) {
         uint32_t w[4];
         philox4x32_10(p.k0, p.k1, id_lo, id_hi, episode, batch * 32u + (uint32_t)lane, w);
-        for (int blk = 0; blk < 32 && cnt < K; ++blk) {
-            uint32_t v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(FULL, w[i], blk);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t x = (v[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                const uint32_t m = x * (uint32_t)HW;
-                const uint32_t d = m >> 16;
-                const uint32_t bit = 1u << (d & 31u);
-                const bool ok = (cnt < K) && ((m & 0xFFFFu) >= thresh) && (lane == (int)(d >> 5)) &&
-                                !((forb | chosen) & bit);
-                if (ok) chosen |= bit;
-                cnt += __any_sync(FULL, ok) ? 1 : 0;
+        for (int r = 0; r < 8; ++r) {
+            if (cnt >= K) break;
+            const uint32_t x = (w[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+            const uint32_t m = x * (uint32_t)HW;
+            const uint32_t d = m >> 16;
+            const int owner = (int)(d >> 5);
+            const uint32_t bit = 1u << (d & 31u);
+            const uint32_t occ = __shfl_sync(FULL, forb | chosen, owner);
+            const bool cand = ((m & 0xFFFFu) >= thresh) && !(occ & bit);
+            const uint32_t same = __match_any_sync(FULL, cand ? d : (0x10000u + (uint32_t)lane));
+            const bool novel = cand && ((same & lt_mask) == 0u);
+            const uint32_t B = __ballot_sync(FULL, novel);
+            const int need = K - cnt;
+            const bool keep = novel && (__popc(B & lt_mask) < need);
+            const int got = __popc(B);
+            cnt += got < need ? got : need;
+            for (int wd = 0; wd < wpb; ++wd) {
+                const uint32_t nb = __reduce_or_sync(FULL, (keep && owner == wd) ? bit : 0u);
+                if (lane == wd) chosen |= nb;
             }
         }
     }
@@ -110,24 +127,24 @@ __device__ __noinline__ uint32_t sample_mines(const EnvParams &p, long long env_
 // ---------------------------------------------------------------------------
 // Encoder: _build_obs (env.py:172-192), _compute_action_mask (env.py:194-196)
 // and the aux maps of train_rl.py:205-212, from register-resident bitboards.
-// Vector path (HW % 4 == 0): lane handles cells [4q, 4q+4) of every plane, one
-// st.global.cs.v4.f32 per plane -> each warp store covers 512 contiguous bytes.
+// Vector path (HW % 4 == 0): lane handles cells [4q, 4q+4) of every plane; the
+// four {0,1} cells of a plane are a nibble that indexes a 16-entry float4 table
+// in shared memory, so each 16-byte store costs two LOP3, one LDS.128 and one
+// st.global.cs.v4.f32 (every warp store covers 512 contiguous bytes).
 // ---------------------------------------------------------------------------
 template <int CW, int CHW>
 __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, int lane, uint32_t R,
                                              uint32_t M, uint32_t F, int first, const Planes &pl,
-                                             const Geo &g)
+                                             const Geo &g, const float4 *__restrict__ lut)
 {
     const int HW = CHW ? CHW : p.HW;
-    const uint32_t Lm = first ? M : 0u;                               // train_rl.py:206-208
-    const uint32_t Vm = first ? (~R & ~F & g.valid) : 0u;             // train_rl.py:209
-    const uint32_t NR = ~R & g.valid;                                 // env.py:195
     if ((HW & 3) == 0) {
         const int quads = HW >> 2;
         float4 *obs_b = p.obs ? reinterpret_cast<float4 *>(p.obs + b * (long long)(MSW_OBS_CHANNELS * HW)) : nullptr;
         uint32_t *mask_b = p.mask ? reinterpret_cast<uint32_t *>(p.mask + b * (long long)HW) : nullptr;
         float4 *lab_b = p.labels ? reinterpret_cast<float4 *>(p.labels + b * (long long)HW) : nullptr;
         uint32_t *val_b = p.valid ? reinterpret_cast<uint32_t *>(p.valid + b * (long long)HW) : nullptr;
+        const uint32_t gate = first ? 15u : 0u;                       // env.py:181
 #pragma unroll 2
         for (int q0 = 0; q0 < quads; q0 += 32) {
             const int q = q0 + lane;
@@ -135,32 +152,34 @@ __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, in
             const int src = (act ? q : 0) >> 3;
             const int sh = (q & 7) << 2;
             const uint32_t r4 = (__shfl_sync(FULL, R, src) >> sh) & 15u;
-            const uint32_t a0 = (__shfl_sync(FULL, pl.c0, src) >> sh) & 15u;
-            const uint32_t a1 = (__shfl_sync(FULL, pl.c1, src) >> sh) & 15u;
-            const uint32_t a2 = (__shfl_sync(FULL, pl.c2, src) >> sh) & 15u;
-            const uint32_t a3 = (__shfl_sync(FULL, pl.c3, src) >> sh) & 15u;
-            const uint32_t n4 = (__shfl_sync(FULL, NR, src) >> sh) & 15u;
-            uint32_t l4 = 0, v4 = 0;
-            if (lab_b) l4 = (__shfl_sync(FULL, Lm, src) >> sh) & 15u;
-            if (val_b) v4 = (__shfl_sync(FULL, Vm, src) >> sh) & 15u;
+            const uint32_t a0 = __shfl_sync(FULL, pl.c0, src) >> sh;
+            const uint32_t a1 = __shfl_sync(FULL, pl.c1, src) >> sh;
+            const uint32_t a2 = __shfl_sync(FULL, pl.c2, src) >> sh;
+            const uint32_t a3 = __shfl_sync(FULL, pl.c3, src) >> sh;
+            uint32_t l4 = 0, f4 = 0;
+            if (lab_b) l4 = (__shfl_sync(FULL, M, src) >> sh) & gate;           // train_rl.py:206-208
+            if (val_b && p.flags) f4 = (__shfl_sync(FULL, F, src) >> sh) & 15u;
             if (!act) continue;
+            const uint32_t n4 = r4 ^ 15u;                                        // env.py:195
             if (obs_b) {
-                const uint32_t g4 = first ? r4 : 0u;                  // env.py:181
+                const uint32_t g4 = r4 & gate;
                 float4 *o = obs_b + q;
-                __stcs(o, nib_to_f4(r4));
+                __stcs(o, lut[r4]);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    const uint32_t m = g4 & ((k & 1) ? a0 : ~a0) & ((k & 2) ? a1 : ~a1) &
-                                       ((k & 4) ? a2 : ~a2) & ((k & 8) ? a3 : ~a3);
-                    __stcs(o + (1 + k) * quads, nib_to_f4(m));
+                    const uint32_t lo = g4 & ((k & 1) ? a0 : ~a0) & ((k & 2) ? a1 : ~a1);
+                    const uint32_t m = lo & ((k & 4) ? a2 : ~a2) & ((k & 8) ? a3 : ~a3);
+                    __stcs(o + (1 + k) * quads, lut[m]);
                 }
             }
             if (mask_b) __stcs(mask_b + q, nib_to_b4(n4));
-            if (lab_b) __stcs(lab_b + q, nib_to_f4(l4));
-            if (val_b) __stcs(val_b + q, nib_to_b4(v4));
+            if (lab_b) __stcs(lab_b + q, lut[l4]);
+            if (val_b) __stcs(val_b + q, nib_to_b4(n4 & ~f4 & gate));            // train_rl.py:209
         }
     } else {
         // Scalar path for boards whose planes are not 16-byte multiples (e.g. 5x7, 9x9).
+        const uint32_t Lm = first ? M : 0u;
+        const uint32_t Vm = first ? (~R & ~F & g.valid) : 0u;
         const int wpb = (HW + 31) >> 5;
         float *obs_b = p.obs ? p.obs + b * (long long)(MSW_OBS_CHANNELS * HW) : nullptr;
         uint8_t *mask_b = p.mask ? p.mask + b * (long long)HW : nullptr;
@@ -192,10 +211,39 @@ __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, in
 // The fused env kernel.  MODE_STEP: VecMinesweeper.step (env.py:479-511);
 // MODE_RESET: VecMinesweeper.reset (env.py:468-477); MODE_ENCODE: observation
 // of the current state.  CW/CHW != 0 specialise the board shape at compile time.
+// Each warp walks boards b, b+total_warps, ... and issues the loads of its next
+// board before it starts computing on the current one, so the ~1 us of HBM/L2
+// latency on the state is hidden behind the step logic and the stores.
 // ---------------------------------------------------------------------------
-template <int MODE, int CW, int CHW>
-__global__ void __launch_bounds__(256, 4) env_kernel(const __grid_constant__ EnvParams p)
+struct BoardIn {
+    uint32_t M, R, F;
+    int4 meta;                 // first_click_done, step_count, episode_idx, last_new_reveals
+    long long action;
+};
+
+template <int MODE>
+__device__ __forceinline__ BoardIn load_board(const EnvParams &p, long long b, int lane, int wpb)
 {
+    BoardIn in;
+    in.M = in.R = in.F = 0u;
+    in.action = 0;
+    in.meta = __ldg(p.meta + b);
+    if (MODE != MODE_RESET && lane < wpb) {
+        in.M = p.mines[b * wpb + lane];
+        in.R = p.revealed[b * wpb + lane];
+        if (p.flags) in.F = p.flags[b * wpb + lane];
+    }
+    if (MODE == MODE_STEP) in.action = p.a32 ? (long long)__ldg(p.a32 + b) : __ldg(p.a64 + b);
+    return in;
+}
+
+template <int MODE, int CW, int CHW, bool PF, int MINB>
+__global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ EnvParams p)
+{
+    __shared__ float4 s_lut[16];                 // nibble of four {0,1} cells -> four fp32
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = nib_to_f4(threadIdx.x);
+    __syncthreads();
+
     const int lane = threadIdx.x & 31;
     const int W = CW ? CW : p.W;
     const int HW = CHW ? CHW : p.HW;
@@ -208,14 +256,17 @@ __global__ void __launch_bounds__(256, 4) env_kernel(const __grid_constant__ Env
     g.notlast = p.g_notlast[lane];
     const bool own = lane < wpb;
 
-    for (long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < p.n; b += total_warps) {
-        uint32_t M = 0, R = 0, F = 0;
-        int4 meta = p.meta[b];          // first_click_done, step_count, episode_idx, last_new_reveals
-        if (MODE != MODE_RESET && own) {
-            M = p.mines[b * wpb + lane];
-            R = p.revealed[b * wpb + lane];
-            if (p.flags) F = p.flags[b * wpb + lane];
-        }
+    long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (b >= p.n) return;
+    BoardIn cur = load_board<MODE>(p, b, lane, wpb);
+    while (true) {
+        const long long nb = b + total_warps;
+        const bool more = nb < p.n;
+        BoardIn nxt;
+        if (PF && more) nxt = load_board<MODE>(p, nb, lane, wpb);   // prefetch: consumed next iteration
+
+        uint32_t M = cur.M, R = cur.R, F = cur.F;
+        const int4 meta = cur.meta;
         int first = meta.x;
         Planes pl = {0u, 0u, 0u, 0u};
 
@@ -234,10 +285,8 @@ __global__ void __launch_bounds__(256, 4) env_kernel(const __grid_constant__ Env
         } else {
             // ---- action decode: cell = action % (H*W), Python modulo (env.py:104-107)
             int cell;
-            if (p.a32) {
-                cell = p.a32[b] % HW;
-            } else {
-                const long long a = p.a64[b];
+            {
+                const long long a = cur.action;
                 cell = (a == (long long)(int)a) ? ((int)a % HW) : (int)(a % (long long)HW);
             }
             if (cell < 0) cell += HW;
@@ -308,7 +357,11 @@ __global__ void __launch_bounds__(256, 4) env_kernel(const __grid_constant__ Env
                 if (mines_dirty || done) p.mines[b * wpb + lane] = M;
             }
         }
-        encode_board<CW, CHW>(p, b, lane, R, M, F, first, pl, g);
+        encode_board<CW, CHW>(p, b, lane, R, M, F, first, pl, g, s_lut);
+        if (!more) break;
+        if (PF) cur = nxt;
+        else cur = load_board<MODE>(p, nb, lane, wpb);
+        b = nb;
     }
 }
 
@@ -467,22 +520,99 @@ static int set_encode_out(EnvParams &p, const msw_encode_out *out, bool require)
     return MSW_OK;
 }
 
-static inline int grid_for(long long n)
+// Launch shape.  Stores reach full HBM write bandwidth only when CTAs are handed out
+// dynamically (profiles/r01_store_probe2.txt: a static one-wave grid tops out near 6.0 TB/s,
+// the same stores from many short CTAs reach 6.9-7.0 TB/s), so the grid is sized from
+// boards-per-warp rather than from the SM count.  Development knobs (environment, read once):
+//   MSW_BLOCK        threads per CTA (32..256; default 32: one warp per CTA, so a slow board --
+//                    a deep flood fill, a board draw -- never holds other warps' slots)
+//   MSW_BPW          boards per warp (default 3, with the next board's state prefetched);
+//                    0 = use MSW_CTAS_PER_SM
+// Sweep: profiles/r01_sweep_launch_shape.txt.
+//   MSW_CTAS_PER_SM  cap the grid at that many CTAs per SM (warps stride over boards)
+static inline int env_int(const char *name, int dflt)
 {
-    const long long blocks = (n + 7) / 8;                     // 8 warps (boards) per 256-thread CTA
-    const long long cap = (long long)sm_count() * 8;          // persistent: <= 8 CTAs per SM, grid-stride
-    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+struct LaunchShape { int block, bpw, cap; };
+
+static inline const LaunchShape &launch_shape_cfg()
+{
+    static LaunchShape c = {0, 0, 0};
+    if (c.block == 0) {
+        int blk = env_int("MSW_BLOCK", 32);
+        if (blk < 32) blk = 32;
+        if (blk > 256) blk = 256;
+        c.block = blk & ~31;
+        c.bpw = env_int("MSW_BPW", 3);
+        c.cap = env_int("MSW_CTAS_PER_SM", 8);
+        if (c.bpw < 0) c.bpw = 0;
+        if (c.cap < 0) c.cap = 0;
+    }
+    return c;
+}
+
+static inline int grid_for(long long n, int *block_out)
+{
+    const LaunchShape &c = launch_shape_cfg();
+    const int wpc = c.block / 32;
+    *block_out = c.block;
+    long long blocks;
+    if (c.bpw > 0) {
+        const long long warps = (n + c.bpw - 1) / c.bpw;
+        blocks = (warps + wpc - 1) / wpc;
+    } else {
+        blocks = (n + wpc - 1) / wpc;
+        if (c.cap > 0) {
+            const long long cap = (long long)sm_count() * c.cap;
+            if (blocks > cap) blocks = cap;
+        }
+    }
+    if (blocks < 1) blocks = 1;
+    if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+    return (int)blocks;
+}
+
+// MSW_VARIANT (development knob, see profiles/): 0 = no prefetch, 4 CTAs/SM (64 regs);
+// 1 = prefetch, 4 CTAs/SM; 2 = prefetch, 3 CTAs/SM (80 regs); 3 = no prefetch, 5 CTAs/SM (48 regs).
+static inline int variant()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("MSW_VARIANT");
+        cached = e ? atoi(e) : 2;
+        if (cached < 0 || cached > 3) cached = 2;
+    }
+    return cached;
+}
+
+template <int MODE, int CW, int CHW>
+static void launch_shape(const EnvParams &p, int grid, int block, cudaStream_t s)
+{
+    if (MODE != MODE_STEP) {
+        env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p);
+        return;
+    }
+    switch (variant()) {
+    case 1: env_kernel<MODE, CW, CHW, true, 4><<<grid, block, 0, s>>>(p); break;
+    case 2: env_kernel<MODE, CW, CHW, true, 3><<<grid, block, 0, s>>>(p); break;
+    case 3: env_kernel<MODE, CW, CHW, false, 5><<<grid, block, 0, s>>>(p); break;
+    default: env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p); break;
+    }
 }
 
 template <int MODE>
 static int launch_env(const EnvParams &p, cudaStream_t s)
 {
     if (p.n == 0) return MSW_OK;
-    const int grid = grid_for(p.n);
+    int block = 256;
+    const int grid = grid_for(p.n, &block);
     if (p.W == 16 && p.HW == 256)
-        env_kernel<MODE, 16, 256><<<grid, 256, 0, s>>>(p);
+        launch_shape<MODE, 16, 256>(p, grid, block, s);
     else
-        env_kernel<MODE, 0, 0><<<grid, 256, 0, s>>>(p);
+        launch_shape<MODE, 0, 0>(p, grid, block, s);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }
@@ -577,7 +707,7 @@ extern "C" int msw_unpack_state(const msw_env_desc *desc, const msw_state *st, i
     if (rc) return rc;
     q.o_mine = mine; q.o_rev = revealed; q.o_flags = flags; q.o_counts = counts;
     if (n == 0) return MSW_OK;
-    unpack_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(q);
+    unpack_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(q);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

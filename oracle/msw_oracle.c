@@ -79,9 +79,9 @@ void orc_philox4x32_10(uint32_t k0, uint32_t k1, const uint32_t c[4], uint32_t o
  * First-click-safe placement, env.py:280-312.  The forbidden set and the
  * "relax to the clicked cell only" fallback follow the reference; the choice
  * of the subset uses the counter-based sampler specified in DESIGN.md:
- * 16-bit Lemire draws over all cells, rejecting forbidden/already-chosen
- * cells, choosing the complement when more than half the allowed cells are
- * mines.  Sequential rejection sampling without replacement is exactly
+ * 16-bit Lemire draws over all cells in Philox stream order, rejecting
+ * forbidden/already-chosen cells, choosing the complement when more than half
+ * the allowed cells are mines.  Sequential rejection sampling without replacement is exactly
  * uniform over mine_count-subsets of the allowed cells.
  */
 void orc_place_mines(const orc_cfg *cfg, int64_t env_id, uint32_t episode,
@@ -118,19 +118,23 @@ void orc_place_mines(const orc_cfg *cfg, int64_t env_id, uint32_t episode,
     const uint32_t thresh = 65536u % (uint32_t)HW;
     const uint32_t k0 = (uint32_t)cfg->seed, k1 = (uint32_t)(cfg->seed >> 32);
     uint32_t ctr[4] = { (uint32_t)(uint64_t)env_id, (uint32_t)((uint64_t)env_id >> 32), episode, 0 };
-    uint32_t w[4] = {0, 0, 0, 0};
-    uint32_t have_blk = 0xFFFFFFFFu;
+    /* Draw p is 16-bit slot (p%256)/32 of Philox block 32*(p/256) + p%32 ("board
+     * sampler"): 32 consecutive draws come from 32 consecutive counter blocks. */
+    uint32_t w[32][4];
+    uint32_t have_batch = 0xFFFFFFFFu;
     uint32_t p = 0;
     int cnt = 0;
     while (cnt < K) {
-        uint32_t blk = p >> 3, j = p & 7u;
+        const uint32_t batch = p >> 8, slot = (p & 255u) >> 5, ln = p & 31u;
         ++p;
-        if (blk != have_blk) {
-            ctr[3] = blk;
-            orc_philox4x32_10(k0, k1, ctr, w);
-            have_blk = blk;
+        if (batch != have_batch) {
+            for (uint32_t l = 0; l < 32; ++l) {
+                ctr[3] = batch * 32u + l;
+                orc_philox4x32_10(k0, k1, ctr, w[l]);
+            }
+            have_batch = batch;
         }
-        uint32_t x = (w[j >> 1] >> (16u * (j & 1u))) & 0xFFFFu;
+        uint32_t x = (w[ln][slot >> 1] >> (16u * (slot & 1u))) & 0xFFFFu;
         uint32_t m = x * (uint32_t)HW;
         if ((m & 0xFFFFu) < thresh) continue;
         uint32_t d = m >> 16;
