@@ -47,6 +47,7 @@ struct EnvParams {
     uint8_t *mask;
     float *labels;
     uint8_t *valid;
+    int vec_mode;                    // 1: 4 cells / lane, 128-bit stores (HW % 4 == 0); 0: scalar
     // per-lane geometry
     uint32_t g_valid[32], g_notcol0[32], g_notlast[32];
 };
@@ -138,7 +139,7 @@ __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, in
                                              const Geo &g, const float4 *__restrict__ lut)
 {
     const int HW = CHW ? CHW : p.HW;
-    if ((HW & 3) == 0) {
+    if (p.vec_mode == 1) {
         const int quads = HW >> 2;
         float4 *obs_b = p.obs ? reinterpret_cast<float4 *>(p.obs + b * (long long)(MSW_OBS_CHANNELS * HW)) : nullptr;
         uint32_t *mask_b = p.mask ? reinterpret_cast<uint32_t *>(p.mask + b * (long long)HW) : nullptr;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, in
 struct BoardIn {
     uint32_t M, R, F;
     int4 meta;                 // first_click_done, step_count, episode_idx, last_new_reveals
-    long long action;
+    int a_lo, a_hi;            // raw action words; decoded at use so the prefetch never waits
 };
 
 template <int MODE>
@@ -226,14 +227,22 @@ __device__ __forceinline__ BoardIn load_board(const EnvParams &p, long long b, i
 {
     BoardIn in;
     in.M = in.R = in.F = 0u;
-    in.action = 0;
+    in.a_lo = in.a_hi = 0;
     in.meta = __ldg(p.meta + b);
     if (MODE != MODE_RESET && lane < wpb) {
         in.M = p.mines[b * wpb + lane];
         in.R = p.revealed[b * wpb + lane];
         if (p.flags) in.F = p.flags[b * wpb + lane];
     }
-    if (MODE == MODE_STEP) in.action = p.a32 ? (long long)__ldg(p.a32 + b) : __ldg(p.a64 + b);
+    if (MODE == MODE_STEP) {
+        if (p.a32) {
+            in.a_lo = __ldg(p.a32 + b);
+        } else {
+            const int2 a = __ldg(reinterpret_cast<const int2 *>(p.a64) + b);
+            in.a_lo = a.x;
+            in.a_hi = a.y;
+        }
+    }
     return in;
 }
 
@@ -285,9 +294,11 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
         } else {
             // ---- action decode: cell = action % (H*W), Python modulo (env.py:104-107)
             int cell;
-            {
-                const long long a = cur.action;
-                cell = (a == (long long)(int)a) ? ((int)a % HW) : (int)(a % (long long)HW);
+            if (p.a32 || cur.a_hi == (cur.a_lo >> 31)) {
+                cell = cur.a_lo % HW;                                     // fits int32
+            } else {
+                const long long a = ((long long)cur.a_hi << 32) | (unsigned int)cur.a_lo;
+                cell = (int)(a % (long long)HW);
             }
             if (cell < 0) cell += HW;
             const uint32_t startmask = (lane == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
@@ -512,10 +523,14 @@ static int set_encode_out(EnvParams &p, const msw_encode_out *out, bool require)
 {
     if (!out) return require ? fail(MSW_ERR_NULL, "encode outputs are NULL") : MSW_OK;
     p.obs = out->obs; p.mask = out->mask; p.labels = out->mine_labels; p.valid = out->mine_valid;
+    const uintptr_t f = (uintptr_t)p.obs | (uintptr_t)p.labels, m = (uintptr_t)p.mask | (uintptr_t)p.valid;
+    p.vec_mode = 0;
     if ((p.HW & 3) == 0) {
-        if (((uintptr_t)p.obs & 15u) || ((uintptr_t)p.labels & 15u) || ((uintptr_t)p.mask & 3u) ||
-            ((uintptr_t)p.valid & 3u))
+        if ((f & 15u) || (m & 3u))
             return fail(MSW_ERR_ALIGN, "obs/mine_labels must be 16-byte and mask/mine_valid 4-byte aligned");
+        // (8 cells / lane with 256-bit st.global.v8 stores was measured 8% SLOWER than this
+        // 128-bit path on B200 -- profiles/r01_sweep_vec256.txt -- and was removed.)
+        p.vec_mode = 1;
     }
     return MSW_OK;
 }
