@@ -265,6 +265,9 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     e2e_full_max = reduce_max(e2e_full_s)
     ms_kernel_max = reduce_max(ms_kernel)
 
+    gae_info = None if args.no_gae else bench_gae(torch, m, dev)
+    roll_info = None if args.no_rollout else bench_rollout(torch, m, dev, rank, world, reduce_max)
+
     if rank != 0:
         return
     total_envs = N * world
@@ -305,6 +308,8 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
                     "copied to pinned host memory every step; PCIe-bound by construction",
         },
         "gpu_launches": 2 * K,
+        "gae": gae_info,
+        "rollout": roll_info,
         "clocks": clocks,
         "episodes_finished_in_e2e": episodes,
     }
@@ -323,6 +328,69 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def bench_gae(torch, m, dev):
+    """msw_gae at C3 size (T=128, N=8192; BASELINE.md section 4 inputs), CUDA-event timed."""
+    T, N = 128, 8192
+    g = torch.Generator(device=dev).manual_seed(0)
+    buf = m.RolloutBuffer(N, T, (1, 1, 1), 1, dev)
+    consts = torch.tensor([-1e-4, -1.0 - 1e-4, 1.0 - 1e-4], dtype=torch.float64).float().to(dev)
+    dones = torch.rand((T * N,), device=dev, generator=g) < 0.15
+    buf.dones.copy_(dones)
+    buf.rewards.copy_(torch.where(dones, consts[torch.randint(1, 3, (T * N,), device=dev, generator=g)], consts[0]))
+    buf.values.copy_(0.5 * torch.randn((T * N,), device=dev, generator=g))
+    last = 0.5 * torch.randn((N,), device=dev, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > L2: inputs come from HBM
+    times = []
+    for i in range(13):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        buf.compute_gae(last, 0.995, 0.95)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(a.elapsed_time(b))
+    ms = float(np.median(times))
+    nbytes = 17 * T * N + 4 * N
+    peak, _ = measured_peak_gbs()
+    return {"T": T, "N": N, "kernel_us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
+            "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "l2": "256 MB flush write between launches",
+            "note": "latency-bound at this size: 8,192 independent chains of 128 dependent steps"}
+
+
+def bench_rollout(torch, m, dev, rank, world, reduce_max):
+    """BASELINE.json configs[2] (C3): PPO rollout + GAE, medium residual CNN (96 ch x 5 blocks,
+    random init), fp16 autocast, fused masked sampler, 8,192 envs x 128 steps per GPU, aux maps on."""
+    N, T = 8192, 128
+    torch.manual_seed(0)
+    cfg = env_cfg(m)
+    vec = m.VecMinesweeper(N, cfg, seed=0, api="torch", env_id_base=rank * N)
+    model = m.build_model("cnn_residual", obs_shape=(10, H, W),
+                          model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).to(dev)
+    model = model.to(memory_format=torch.channels_last)
+    col = m.RolloutCollector(vec, T, aux_maps=True)
+    times = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        buf, aux = col.collect(model)
+        b.record()
+        buf.compute_gae(aux["last_values"], 0.995, 0.95)
+        c.record()
+        torch.cuda.synchronize()
+        if i >= 1:
+            times.append((a.elapsed_time(b), b.elapsed_time(c)))
+    ms_roll = float(np.mean([t[0] for t in times]))
+    ms_gae = float(np.mean([t[1] for t in times]))
+    ms = reduce_max(ms_roll + ms_gae)
+    flops = 0.44e9 * N * (T + 1)                      # SURVEY section 2: ~0.44 GFLOP / board / forward
+    return {"workload": "C3", "frames_per_s": world * N * T / (ms / 1e3), "envs_per_gpu": N, "steps": T,
+            "ms_rollout": ms_roll, "ms_gae": ms_gae, "dtype": "fp16 autocast (cuDNN), env/GAE/sampler in CUDA",
+            "model": "cnn_residual 96x5 (950,947 params), random init, train mode (dropout on, as the reference)",
+            "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": int(buf.dones.sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,6 +400,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value and roofline only")
+    ap.add_argument("--no-gae", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

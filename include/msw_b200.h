@@ -152,6 +152,18 @@ int msw_gae(const float *rewards, const float *values, const uint8_t *dones,
             int64_t T, int64_t N, float gamma_f32, float gamma_lam_f32,
             int32_t last_values_prescaled, void *stream);
 
+/* Fused masked categorical sampler, replacing
+ * train_rl.py:229-235 + the int64->int32 conversion of :239: logits [n][A]
+ * (logits_dtype 0 = f32, 1 = f16, 2 = bf16) are masked with the reference's
+ * fill value (-1e9 for f32, -1e4 for half types), soft-maxed in fp32, one
+ * action per row is drawn by inverse CDF with a Philox uniform keyed by
+ * (seed, row_id_base + row, step_index), and log_prob(action) is returned.
+ * Writes whichever of actions64 / actions32 / logp is non-NULL. */
+int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *mask,
+                      int64_t n, int32_t A, uint64_t seed, uint64_t step_index,
+                      int64_t row_id_base, int64_t *actions64, int32_t *actions32,
+                      float *logp, void *stream);
+
 /* Host-buffer form of msw_step for callers that keep the reference's NumPy
  * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):
  * `h_actions32` and every non-NULL h_* output are pinned host buffers; `io`

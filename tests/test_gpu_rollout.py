@@ -1,0 +1,104 @@
+"""Fused masked sampler (msw_masked_sample) and the device-resident collector (rollout.py),
+the rows of SURVEY section 8 next to the env path (a12, f1).  Needs a B200."""
+import numpy as np
+import pytest
+
+import parity as P
+
+pytestmark = pytest.mark.gpu
+LOGP_TOL = 2e-5      # fp32 log-softmax vs torch's fp32 log_softmax of the same masked logits
+
+
+@pytest.mark.parametrize("dtype_name", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("A", [256, 480, 64, 35, 1024])
+def test_masked_sample_logp_and_validity(dtype_name, A):
+    import torch
+    import minesweeper_ppo_b200 as m
+    dt = getattr(torch, dtype_name)
+    g = torch.Generator(device="cuda").manual_seed(A)
+    n = 4096
+    logits = (3.0 * torch.randn((n, A), device="cuda", generator=g)).to(dt)
+    mask = torch.rand((n, A), device="cuda", generator=g) < 0.4
+    mask[:, 0] |= ~mask.any(1)                                   # at least one legal action per row
+    mask[5] = False; mask[5, A - 1] = True                       # single legal action
+    a64, a32, logp = m.masked_sample(logits, mask, seed=7, step_index=3)
+    assert torch.equal(a64.to(torch.int32), a32)
+    assert bool(mask.gather(1, a64[:, None]).all()), "sampled an illegal action"
+    assert int(a64[5]) == A - 1
+    neg = -1e9 if dt == torch.float32 else -1e4                  # train_rl.py:229-232
+    ref = torch.log_softmax(logits.masked_fill(~mask, neg).float(), dim=-1).gather(1, a64[:, None])[:, 0]
+    assert float((logp - ref).abs().max()) <= LOGP_TOL
+    # deterministic in (seed, step, row); different step -> different draws
+    b64, _, _ = m.masked_sample(logits, mask, seed=7, step_index=3)
+    c64, _, _ = m.masked_sample(logits, mask, seed=7, step_index=4)
+    assert torch.equal(a64, b64) and not torch.equal(a64, c64)
+
+
+def test_masked_sample_distribution_chi2():
+    import torch
+    from scipy import stats
+    import minesweeper_ppo_b200 as m
+    A, n = 16, 400_000
+    row = torch.tensor([0.3, -1.0, 2.0, 0.0, 1.5, -3.0, 0.7, 0.1, 9.0, -0.2, 1.1, 0.4, -0.6, 2.2, 0.9, 0.0])
+    mask_row = torch.ones(A, dtype=torch.bool); mask_row[8] = False; mask_row[3] = False
+    logits = row.cuda().repeat(n, 1).half()
+    mask = mask_row.cuda().repeat(n, 1).contiguous()
+    a64, _, _ = m.masked_sample(logits, mask, seed=123, step_index=0)
+    counts = torch.bincount(a64, minlength=A).cpu().numpy().astype(np.float64)
+    assert counts[8] == 0 and counts[3] == 0
+    p = torch.softmax(logits[0].float().masked_fill(~mask[0], -1e4), 0).cpu().numpy().astype(np.float64)
+    keep = p > 1e-12
+    chi2 = ((counts[keep] - n * p[keep]) ** 2 / (n * p[keep])).sum()
+    assert stats.chi2.sf(chi2, df=int(keep.sum()) - 1) > 1e-4, chi2
+
+
+def test_collector_buffer_is_self_consistent(oracle):
+    """collect_rollout on device: replay the recorded actions through the CPU oracle (same board
+    sampler spec, same seed) and require every buffer field the env produced to match bit for bit."""
+    import os
+    import torch
+    import minesweeper_ppo_b200 as m
+    torch.manual_seed(0)
+    N, T = 256, 24
+    cfg = m.EnvConfig(H=16, W=16, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    vec = m.VecMinesweeper(N, cfg, seed=11, api="torch")
+    model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
+                          model_cfg=dict(stem_channels=32, blocks=2, dropout=0.0, value_hidden=64)).cuda().eval()
+    buf, aux = m.collect_rollout(vec, model, T, torch.device("cuda"), aux_mine_weight=0.05, aux_mine_calib_weight=0.01)
+    assert aux["last_values"].shape == (N,) and aux["last_values"].dtype == torch.float16     # train_rl.py:272-277
+    assert set(aux["timings"]) >= {"steps", "rollout_total_s"}
+    buf.compute_gae(aux["last_values"], 0.995, 0.95)
+    c = lambda t_: t_.cpu().numpy()
+    acts = c(buf.actions).reshape(T, N)
+    ref = oracle.OracleVecEnv(N, cfg, seed=11, nthreads=os.cpu_count() or 1, aux_maps=True)
+    b = ref.reset()                   # collect_rollout resets at the start of every rollout (train_rl.py:163)
+    obs, mask, lab, val = b["obs"], b["action_mask"], ref.mine_labels, ref.mine_valid
+    for t in range(T):
+        s = slice(t * N, (t + 1) * N)
+        P.assert_bits_equal(c(buf.obs[s]), obs, f"slot {t} obs")
+        P.assert_bits_equal(c(buf.action_mask[s]), mask, f"slot {t} mask")
+        P.assert_bits_equal(c(buf.mine_labels[s]), lab, f"slot {t} labels")
+        P.assert_bits_equal(c(buf.mine_valid[s]), val, f"slot {t} valid")
+        assert mask[np.arange(N), acts[t]].all(), "policy sampled a revealed cell"
+        bb, r, d, _ = ref.step(acts[t], tensor_infos=True)
+        P.assert_bits_equal(c(buf.rewards[s]), r, f"slot {t} rewards")
+        P.assert_bits_equal(c(buf.dones[s]), d, f"slot {t} dones")
+        obs, mask, lab, val = bb["obs"], bb["action_mask"], ref.mine_labels, ref.mine_valid
+    # GAE on the collected buffer == oracle GAE with the fp16-bootstrap rule (buffers.py:88-90)
+    lv16 = aux["last_values"]
+    T_, N_ = T, N
+    r_np, v_np, d_np = c(buf.rewards).reshape(T_, N_), c(buf.values).reshape(T_, N_), c(buf.dones).reshape(T_, N_)
+    gv_last = (0.995 * lv16).float().cpu().numpy()              # torch's own fp16 multiply
+    # oracle GAE takes last_values and multiplies by gamma in fp32; emulate the prescaled first step by
+    # folding it into the reward of the last row: r' = r + gv_last*nnt, last_values = 0
+    nnt = 1.0 - d_np[-1].astype(np.float32)
+    r2 = r_np.copy(); r2[-1] = (r_np[-1] + gv_last * nnt).astype(np.float32)
+    adv, ret = oracle.gae(r2, v_np, d_np, np.zeros(N_, np.float32), 0.995, 0.95)
+    P.assert_bits_equal(c(buf.advantages).reshape(T_, N_), adv, "advantages")
+    P.assert_bits_equal(c(buf.returns).reshape(T_, N_), ret, "returns")
+    # second rollout reuses nothing stale
+    col = m.RolloutCollector(vec, T, aux_maps=False)
+    b1, _ = col.collect(model)
+    a1 = b1.actions.clone()
+    b2, _ = col.collect(model)
+    assert not torch.equal(a1, b2.actions)
