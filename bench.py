@@ -35,6 +35,21 @@ ENVS_PER_GPU = 65536
 # algorithmic bytes per env-step at the boundary (fp32 reference layout):
 # obs 40*HW + mask HW + reward 4 + done 1 + action 4
 BYTES_PER_STEP = 41 * H * W + 9          # 10,505 B
+WORKLOAD = "C2"
+
+
+def set_workload(name: str, envs):
+    """C2 = BASELINE.json configs[1] (the bench line); C4 = configs[3], Expert 16x30x99 boards,
+    4,194,304 envs sharded over 8 GPUs = 524,288 per GPU (a parity-test size, offered for sweeps)."""
+    global H, W, MINES, ENVS_PER_GPU, BYTES_PER_STEP, WORKLOAD
+    if name == "C4":
+        H, W, MINES, ENVS_PER_GPU = 16, 30, 99, 524288
+    elif name != "C2":
+        raise SystemExit(f"unknown workload {name}")
+    WORKLOAD = name
+    if envs:
+        ENVS_PER_GPU = int(envs)
+    BYTES_PER_STEP = 41 * H * W + 9
 
 
 def env_cfg(mod):
@@ -153,12 +168,13 @@ def run_reference_arm(args, rank: int, world: int):
     n = int(max(1024, min(ENVS_PER_GPU, rate * budget_s / max(1, args.steps + args.warmup))))
     n = 1 << (n.bit_length() - 1)
     value, total, per_step = cpu_env_steps_per_s(n, args.steps, args.warmup, threads)
-    sample = f"{n} envs x {args.steps} steps, 16x16x40 random valid actions, oracle/msw_oracle.c (C port), {threads} threads"
+    sample = f"{n} envs x {args.steps} steps, {H}x{W}x{MINES} random valid actions, oracle/msw_oracle.c (C port), {threads} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2", "board": "16x16x40", "envs_sampled": n, "actions": "uniform random valid cell"},
+        "config": {"workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_sampled": n,
+                   "actions": "uniform random valid cell"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -166,7 +182,7 @@ def run_reference_arm(args, rank: int, world: int):
                 "C restatement of its algorithm (oracle/), multi-threaded over envs -- a much FASTER baseline than "
                 "the reference itself (about 2e4 env-steps/s on one core, BASELINE.md section 2)",
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -177,10 +193,10 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    N = args.envs
+    N = ENVS_PER_GPU
     K, Wm = args.steps, args.warmup
     cfg = env_cfg(m)
-    ring = 4                                   # rollout-buffer slots the obs/mask stream into
+    ring = 4 if WORKLOAD == "C2" else 2        # rollout-buffer slots the obs/mask stream into
 
     def make_env():
         return m.VecMinesweeper(N, cfg, seed=0, api="torch", env_id_base=rank * N)
@@ -274,21 +290,21 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     value = total_envs * K / (ms_total_max / 1e3)
     peak, peak_src = measured_peak_gbs()
     achieved = BYTES_PER_STEP * N / (ms_kernel_max / 1e3) / 1e9
-    traffic = profiled_traffic()
+    traffic = profiled_traffic() if (WORKLOAD == "C2" and N == 65536) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {
-            "workload": "C2", "board": "16x16x40", "envs_per_gpu": N, "envs_total": total_envs,
+            "workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_per_gpu": N, "envs_total": total_envs,
             "actions": "uniform random valid cell per env per step, generated on device (msw_random_actions)",
-            "auto_reset": True, "obs_layout": "fp32 [N,10,16,16] + bool mask [N,256] (reference layout)",
+            "auto_reset": True, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
             "l2": f"each step writes {BYTES_PER_STEP * N / 1e6:.0f} MB of obs/mask into a ring of {ring} slots "
                   "(>> 126 MB L2), no explicit flush",
             "parallelism": f"env shards, {world} rank(s), no data-path collective",
         },
         "roofline": {
-            "bound": "hbm", "kernel": "msw::env_kernel<MODE_STEP,16,256>", "achieved": achieved, "peak": peak,
+            "bound": "hbm", "kernel": f"msw::env_kernel<MODE_STEP,{W},{H * W}>", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": BYTES_PER_STEP * N, "kernel_ms": ms_kernel_max,
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
@@ -325,7 +341,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
                       "oracle/msw_oracle.c (C restatement of env.py/env_numba.py; the Python reference itself runs "
                       "~2e4 env-steps/s on one core, BASELINE.md section 2)",
         }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def bench_gae(torch, m, dev):
@@ -391,26 +407,63 @@ def bench_rollout(torch, m, dev, rank, world, reduce_max):
             "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": int(buf.dones.sum())}
 
 
+class _QuietStdout:
+    """Route fd 1 to stderr while the benchmark runs (NCCL / library banners must not precede the
+    JSON line on stdout); `emit` writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+    def close(self):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+
+
+OUT = None
+
+
+def emit_json(line: dict):
+    text = json.dumps(line)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value and roofline only")
     ap.add_argument("--no-gae", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    set_workload(args.workload, args.envs)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    OUT = _QuietStdout()
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        try:
+            run_reference_arm(args, rank, world)
+        finally:
+            OUT.close()
         return
 
     if world > 1:
@@ -425,6 +478,7 @@ def main():
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
+        OUT.close()
 
 
 if __name__ == "__main__":

@@ -590,15 +590,16 @@ static inline int grid_for(long long n, int *block_out)
     return (int)blocks;
 }
 
-// MSW_VARIANT (development knob, see profiles/): 0 = no prefetch, 4 CTAs/SM (64 regs);
-// 1 = prefetch, 4 CTAs/SM; 2 = prefetch, 3 CTAs/SM (80 regs); 3 = no prefetch, 5 CTAs/SM (48 regs).
+// MSW_VARIANT (development knob, see profiles/r01_sweep_*.txt): 2 (default) = next-board prefetch,
+// 80 registers; 0 = no prefetch, 64 registers.  (1 = prefetch at 64 registers and 3 = no prefetch at
+// 48 registers were measured slower and dropped.)
 static inline int variant()
 {
     static int cached = -1;
     if (cached < 0) {
         const char *e = getenv("MSW_VARIANT");
         cached = e ? atoi(e) : 2;
-        if (cached < 0 || cached > 3) cached = 2;
+        if (cached != 0) cached = 2;
     }
     return cached;
 }
@@ -610,12 +611,10 @@ static void launch_shape(const EnvParams &p, int grid, int block, cudaStream_t s
         env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p);
         return;
     }
-    switch (variant()) {
-    case 1: env_kernel<MODE, CW, CHW, true, 4><<<grid, block, 0, s>>>(p); break;
-    case 2: env_kernel<MODE, CW, CHW, true, 3><<<grid, block, 0, s>>>(p); break;
-    case 3: env_kernel<MODE, CW, CHW, false, 5><<<grid, block, 0, s>>>(p); break;
-    default: env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p); break;
-    }
+    if (variant() == 2)
+        env_kernel<MODE, CW, CHW, true, 3><<<grid, block, 0, s>>>(p);
+    else
+        env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p);
 }
 
 template <int MODE>
@@ -625,7 +624,9 @@ static int launch_env(const EnvParams &p, cudaStream_t s)
     int block = 256;
     const int grid = grid_for(p.n, &block);
     if (p.W == 16 && p.HW == 256)
-        launch_shape<MODE, 16, 256>(p, grid, block, s);
+        launch_shape<MODE, 16, 256>(p, grid, block, s);       // BASELINE configs 1-3, 5
+    else if (p.W == 30 && p.HW == 480)
+        launch_shape<MODE, 30, 480>(p, grid, block, s);       // BASELINE config 4 (Expert)
     else
         launch_shape<MODE, 0, 0>(p, grid, block, s);
     MSW_CUDA_TRY(cudaGetLastError());
