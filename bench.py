@@ -376,35 +376,47 @@ def bench_gae(torch, m, dev):
 
 def bench_rollout(torch, m, dev, rank, world, reduce_max):
     """BASELINE.json configs[2] (C3): PPO rollout + GAE, medium residual CNN (96 ch x 5 blocks,
-    random init), fp16 autocast, fused masked sampler, 8,192 envs x 128 steps per GPU, aux maps on."""
+    random init), fp16 autocast semantics, fused masked sampler, 8,192 envs x 128 steps per GPU,
+    aux maps on.  Reported twice: with the fused GroupNorm forward (msw_gn_act between cuDNN convs)
+    and with the unchanged eager PyTorch module."""
     N, T = 8192, 128
-    torch.manual_seed(0)
     cfg = env_cfg(m)
-    vec = m.VecMinesweeper(N, cfg, seed=0, api="torch", env_id_base=rank * N)
-    model = m.build_model("cnn_residual", obs_shape=(10, H, W),
-                          model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).to(dev)
-    model = model.to(memory_format=torch.channels_last)
-    col = m.RolloutCollector(vec, T, aux_maps=True)
-    times = []
-    for i in range(3):
-        torch.cuda.synchronize()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        buf, aux = col.collect(model)
-        b.record()
-        buf.compute_gae(aux["last_values"], 0.995, 0.95)
-        c.record()
-        torch.cuda.synchronize()
-        if i >= 1:
-            times.append((a.elapsed_time(b), b.elapsed_time(c)))
-    ms_roll = float(np.mean([t[0] for t in times]))
-    ms_gae = float(np.mean([t[1] for t in times]))
-    ms = reduce_max(ms_roll + ms_gae)
+
+    def run(fused: bool, timed: int):
+        torch.manual_seed(0)
+        vec = m.VecMinesweeper(N, cfg, seed=0, api="torch", env_id_base=rank * N)
+        model = m.build_model("cnn_residual", obs_shape=(10, H, W),
+                              model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).to(dev)
+        col = m.RolloutCollector(vec, T, aux_maps=True, fused=fused)
+        times, episodes = [], 0
+        for i in range(1 + timed):
+            torch.cuda.synchronize()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            buf, aux = col.collect(model)
+            b.record()
+            buf.compute_gae(aux["last_values"], 0.995, 0.95)
+            c.record()
+            torch.cuda.synchronize()
+            if i >= 1:
+                times.append((a.elapsed_time(b), b.elapsed_time(c)))
+            episodes = int(buf.dones.sum())
+        del col, vec, model, buf
+        torch.cuda.empty_cache()
+        ms_roll = float(np.mean([t[0] for t in times]))
+        ms_gae = float(np.mean([t[1] for t in times]))
+        return ms_roll, ms_gae, reduce_max(ms_roll + ms_gae), episodes
+
+    ms_roll, ms_gae, ms, episodes = run(True, 2)
+    s_roll, s_gae, s_ms, _ = run(False, 1)
     flops = 0.44e9 * N * (T + 1)                      # SURVEY section 2: ~0.44 GFLOP / board / forward
     return {"workload": "C3", "frames_per_s": world * N * T / (ms / 1e3), "envs_per_gpu": N, "steps": T,
-            "ms_rollout": ms_roll, "ms_gae": ms_gae, "dtype": "fp16 autocast (cuDNN), env/GAE/sampler in CUDA",
+            "ms_rollout": ms_roll, "ms_gae": ms_gae,
+            "forward": "cuDNN fp16 NHWC convs + fused GroupNorm/ReLU/Dropout2d/residual kernel (msw_gn_act)",
             "model": "cnn_residual 96x5 (950,947 params), random init, train mode (dropout on, as the reference)",
-            "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": int(buf.dones.sum())}
+            "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": episodes,
+            "stock_module_forward": {"frames_per_s": world * N * T / (s_ms / 1e3), "ms_rollout": s_roll,
+                                     "forward": "unchanged eager PyTorch module under fp16 autocast"}}
 
 
 class _QuietStdout:

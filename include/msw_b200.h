@@ -164,6 +164,19 @@ int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *m
                       int64_t row_id_base, int64_t *actions64, int32_t *actions32,
                       float *logp, void *stream);
 
+/* Fused GroupNorm + (fp32 residual add) + ReLU + Dropout2d between the cuDNN
+ * convolutions of the rollout forward (replaces the
+ * eager norm/act/dropout/add/cast kernels of cnn_residual.py:17-27, 50-54
+ * under the fp16 autocast of train_rl.py:222).  x16: fp16 NHWC [n][HW][C] conv
+ * output; statistics and arithmetic in fp32; y16 (fp16 NHWC, the next conv's
+ * input) and/or y32 (fp32 NHWC, the residual stream) are written.  Needs
+ * C % 8 == 0 and (C/G) % 8 == 0; drop_p > 0 applies a Dropout2d channel mask
+ * keyed by (seed, call_id, sample, channel) and is only allowed without res32. */
+int msw_gn_act(const void *x16, const float *res32, const float *gamma, const float *beta,
+               void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
+               float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
+               void *stream);
+
 /* Host-buffer form of msw_step for callers that keep the reference's NumPy
  * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):
  * `h_actions32` and every non-NULL h_* output are pinned host buffers; `io`

@@ -1,0 +1,191 @@
+// msw_gn.cu -- fused GroupNorm + (residual add) + ReLU + Dropout2d for the rollout forward
+// (SURVEY.md section 8, row f4).
+//
+// The reference policy (minesweeper/models/cnn_residual.py:7-27, 50-54) interleaves cuDNN
+// convolutions with GroupNorm / ReLU / Dropout2d / residual adds.  Under fp16 autocast
+// (train_rl.py:222) each conv output is cast to fp32, normalised, activated, dropped, added and
+// cast back to fp16 by ~8 eager ATen kernels per layer; on a B200 those memory-bound kernels take
+// 9x longer than the convolutions themselves (profiles/r01_profile_forward.txt; the reference
+// hides this behind torch.compile, train_rl.py:391-399, which this project may not use).  This
+// kernel does the whole inter-conv step in one pass over the activation:
+//     y = relu( GN(x) [+ residual] ) [* dropout2d mask / (1-p)]
+// x: fp16 NHWC conv output; statistics and arithmetic in fp32 (as autocast runs GroupNorm);
+// outputs: fp16 NHWC (the next conv's input -- the same rounding point as autocast's cast) and,
+// optionally, fp32 NHWC (the residual stream, which the reference keeps in fp32).
+//
+// One CTA per sample: the sample's [HW][C] fp16 tile (48 KB at 16x16x96) is staged in shared
+// memory once, so HBM sees exactly one read and one write of the activation.  Thread (j, r) owns
+// the 8-channel chunk j of pixels r, r+PPB, ...; 8 | channels-per-group, so a thread's chunk lies
+// in one group and its partial sums go to that group with one shared-memory atomic.
+#include "../../include/msw_b200.h"
+#include "msw_common.cuh"
+#include "msw_error.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msw {
+
+struct GnParams {
+    const __half *x;        // [n][HW][C]
+    const float *res;       // nullable [n][HW][C]
+    const float *gamma, *beta;   // [C]
+    __half *y16;            // nullable [n][HW][C]
+    float *y32;             // nullable [n][HW][C]
+    int HW, C, G, cpg, CB, PPB;
+    float eps, inv_count, drop_p, drop_scale;
+    int relu;
+    uint32_t k0, k1, call_lo, call_hi;
+};
+
+__global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);                       // [HW][CB] chunks of 8 halves
+    float *s_sum = reinterpret_cast<float *>(smem_raw + (size_t)p.HW * p.C * 2);   // [G]
+    float *s_sq = s_sum + p.G;
+
+    const int tid = threadIdx.x;
+    const int j = tid % p.CB, r0 = tid / p.CB;
+    const bool active = r0 < p.PPB;
+    const int g = (j * 8) / p.cpg;
+    const long long n = blockIdx.x;
+    const long long base = n * (long long)p.HW * p.CB;                       // in uint4 chunks
+    if (tid < 2 * p.G) s_sum[tid] = 0.0f;
+    __syncthreads();
+
+    // pass 0: stage the sample, accumulate sums
+    float acc = 0.0f;
+    if (active) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.x) + base;
+        for (int r = r0; r < p.HW; r += p.PPB) {
+            const uint4 v = __ldcs(src + r * p.CB + j);
+            tile[r * p.CB + j] = v;
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                acc += f.x + f.y;
+            }
+        }
+        atomicAdd(&s_sum[g], acc);
+    }
+    __syncthreads();
+    const float mean = s_sum[g] * p.inv_count;
+
+    // pass 1: centred second moment (two-pass variance, like torch's RowwiseMoments)
+    if (active) {
+        acc = 0.0f;
+        for (int r = r0; r < p.HW; r += p.PPB) {
+            const uint4 v = tile[r * p.CB + j];
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                const float a = f.x - mean, b = f.y - mean;
+                acc += a * a + b * b;
+            }
+        }
+        atomicAdd(&s_sq[g], acc);
+    }
+    __syncthreads();
+    if (!active) return;
+    const float rstd = rsqrtf(s_sq[g] * p.inv_count + p.eps);
+
+    // per-channel affine folded with the statistics, and the Dropout2d channel mask
+    float a[8], b[8];
+    {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (p.drop_p > 0.0f)
+            philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo, p.call_hi, w);
+        const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = j * 8 + k;
+            const float ga = p.gamma[c] * rstd;
+            a[k] = ga;
+            b[k] = p.beta[c] - mean * ga;
+            const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (p.drop_p > 0.0f) {
+                // relu(z)*s == relu(z*s) for s >= 0, so the mask/scale folds into the affine when no
+                // residual is added (Dropout2d follows ReLU only on that path, cnn_residual.py:20-21)
+                const float s = (u16 < thresh) ? 0.0f : p.drop_scale;
+                a[k] *= s;
+                b[k] *= s;
+            }
+        }
+    }
+    const float4 *res = p.res ? reinterpret_cast<const float4 *>(p.res) + 2 * base : nullptr;
+    uint4 *y16 = p.y16 ? reinterpret_cast<uint4 *>(p.y16) + base : nullptr;
+    float4 *y32 = p.y32 ? reinterpret_cast<float4 *>(p.y32) + 2 * base : nullptr;
+    for (int r = r0; r < p.HW; r += p.PPB) {
+        const int idx = r * p.CB + j;
+        const uint4 v = tile[idx];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            o[2 * k] = fmaf(f.x, a[2 * k], b[2 * k]);
+            o[2 * k + 1] = fmaf(f.y, a[2 * k + 1], b[2 * k + 1]);
+        }
+        if (res) {
+            const float4 q0 = __ldcs(res + 2 * idx), q1 = __ldcs(res + 2 * idx + 1);
+            o[0] += q0.x; o[1] += q0.y; o[2] += q0.z; o[3] += q0.w;
+            o[4] += q1.x; o[5] += q1.y; o[6] += q1.z; o[7] += q1.w;
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.0f);
+        }
+        if (y32) {
+            y32[2 * idx] = make_float4(o[0], o[1], o[2], o[3]);
+            y32[2 * idx + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (y16) {
+            uint4 out;
+            __half2 *oh = reinterpret_cast<__half2 *>(&out);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+            y16[idx] = out;
+        }
+    }
+}
+
+}  // namespace msw
+
+extern "C" int msw_gn_act(const void *x16, const float *res32, const float *gamma, const float *beta, void *y16,
+                          float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
+                          float drop_p, uint64_t seed, uint64_t call_id, void *stream)
+{
+    using namespace msw;
+    if (!x16 || !gamma || !beta || (!y16 && !y32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
+    if (n < 0 || HW < 1 || C < 8 || G < 1 || C % G != 0 || C % 8 != 0 || (C / G) % 8 != 0 || C / 8 > 256 || 2 * G > 256)
+        return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: need C %% 8 == 0, (C/G) %% 8 == 0 (C=%d G=%d HW=%d)", C, G, HW);
+    if (drop_p < 0.0f || drop_p >= 1.0f) return fail(MSW_ERR_ARG, "msw_gn_act: drop_p=%f", drop_p);
+    if (drop_p > 0.0f && res32) return fail(MSW_ERR_ARG, "msw_gn_act: dropout is only defined on the no-residual path");
+    if ((((uintptr_t)x16 | (uintptr_t)res32 | (uintptr_t)y16 | (uintptr_t)y32) & 15u) != 0)
+        return fail(MSW_ERR_ALIGN, "msw_gn_act: tensors must be 16-byte aligned");
+    if (n == 0) return MSW_OK;
+    const size_t smem = (size_t)HW * C * 2 + 2 * (size_t)G * sizeof(float);
+    if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: sample of %zu bytes does not fit shared memory", smem);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        MSW_CUDA_TRY(cudaFuncSetAttribute(gn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    GnParams p;
+    p.x = (const __half *)x16; p.res = res32; p.gamma = gamma; p.beta = beta;
+    p.y16 = (__half *)y16; p.y32 = y32;
+    p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.CB = C / 8; p.PPB = 256 / p.CB;
+    p.eps = eps; p.inv_count = 1.0f / (float)((long long)HW * p.cpg);
+    p.drop_p = drop_p; p.drop_scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    p.relu = relu;
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
+    p.call_lo = (uint32_t)call_id; p.call_hi = (uint32_t)(call_id >> 32);
+    if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: n too large");
+    gn_act_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}

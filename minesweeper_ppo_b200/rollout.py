@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _lib
 from .buffers import RolloutBuffer
 from .env import StepOut, VecMinesweeper
+from .fused_forward import FusedRolloutForward
 
 _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
@@ -61,7 +62,7 @@ def masked_sample(logits: torch.Tensor, mask: torch.Tensor, *, seed: int, step_i
 class RolloutCollector:
     """Reusable collector: owns the buffer and scratch tensors so repeated rollouts allocate nothing."""
 
-    def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool, sample_seed: int = 0):
+    def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool, sample_seed: int = 0, fused: bool = True):
         if vec.api != "torch":
             raise ValueError("RolloutCollector needs VecMinesweeper(api='torch')")
         self.vec, self.steps, self.aux_maps = vec, int(steps), bool(aux_maps)
@@ -73,6 +74,8 @@ class RolloutCollector:
         self.actions32 = torch.empty((N,), dtype=torch.int32, device=dev)
         self.sample_seed = int(sample_seed)
         self.rollouts_done = 0
+        self.fused = bool(fused)          # use FusedRolloutForward when the model supports it
+        self._fused_fwd = None
 
     @torch.no_grad()
     def collect(self, model: nn.Module, autocast: bool = True) -> Tuple[RolloutBuffer, Dict]:
@@ -82,14 +85,20 @@ class RolloutCollector:
         buf._t = 0
         ctx = (lambda: torch.autocast(device_type="cuda", dtype=torch.float16)) if autocast else nullcontext
         base_step = self.rollouts_done * (T + 1)
+        fwd = model
+        if self.fused and autocast and FusedRolloutForward.supports(model):
+            if self._fused_fwd is None or self._fused_fwd.model is not model:
+                self._fused_fwd = FusedRolloutForward(model, seed=self.sample_seed)
+            self._fused_fwd.refresh()                         # weights may have been updated since
+            fwd, ctx = self._fused_fwd, nullcontext
         for t in range(T):
             cur = buf.slot(t)
             rows = slice(t * N, (t + 1) * N)
             with ctx():                                       # train_rl.py:222-227
                 if self.aux_maps:
-                    logits, values, _ = model(cur.obs, return_mine=True)
+                    logits, values, _ = fwd(cur.obs, return_mine=True)
                 else:
-                    logits, values = model(cur.obs)
+                    logits, values = fwd(cur.obs)
             masked_sample(logits, cur.action_mask, seed=self.sample_seed, step_index=base_step + t,
                           row_id_base=vec._desc.env_id_base, actions64=buf.actions[rows],
                           actions32=self.actions32, logp=buf.logp[rows])
@@ -101,9 +110,9 @@ class RolloutCollector:
         buf._t = T
         with ctx():                                           # bootstrap value, train_rl.py:267-277
             if self.aux_maps:
-                _, last_values, _ = model(self.last.obs, return_mine=True)
+                _, last_values, _ = fwd(self.last.obs, return_mine=True)
             else:
-                _, last_values = model(self.last.obs)
+                _, last_values = fwd(self.last.obs)
         self.rollouts_done += 1
         return buf, {"last_values": last_values}
 

@@ -102,3 +102,48 @@ def test_collector_buffer_is_self_consistent(oracle):
     a1 = b1.actions.clone()
     b2, _ = col.collect(model)
     assert not torch.equal(a1, b2.actions)
+
+
+@pytest.mark.parametrize("C,blocks,HW", [(96, 5, (16, 16)), (32, 2, (16, 30)), (128, 1, (8, 8))])
+def test_fused_forward_matches_autocast_module(C, blocks, HW):
+    """msw_gn_act path vs the unchanged module under fp16 autocast (train_rl.py:222): same rounding
+    points, so outputs agree to fp16 resolution.  Dropout off (its RNG stream is not torch's)."""
+    import torch
+    import minesweeper_ppo_b200 as m
+    from minesweeper_ppo_b200.fused_forward import FusedRolloutForward, gn_act
+    torch.manual_seed(1)
+    H, W = HW
+    net = m.build_model("cnn_residual", obs_shape=(10, H, W),
+                        model_cfg=dict(stem_channels=C, blocks=blocks, dropout=0.0, value_hidden=64)).cuda()
+    with torch.no_grad():                                    # non-trivial affine parameters
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.GroupNorm):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.3, 0.3)
+    x = (torch.rand(64, 10, H, W, device="cuda") < 0.3).float()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref = net(x, return_mine=True)
+    got = FusedRolloutForward(net)(x, return_mine=True)
+    for a, b, name in zip(got, ref, ("logits", "value", "mine")):
+        assert a.shape == b.shape and a.dtype == torch.float16, name
+        err = float((a.float() - b.float()).abs().max())
+        scale = float(b.float().abs().max()) + 1e-3
+        assert err <= 2e-2 * scale, (name, err, scale)
+    # the kernel alone vs torch GroupNorm in fp32 on the same fp16 input
+    gn = torch.nn.GroupNorm(C // 16, C).cuda()
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5); gn.bias.uniform_(-0.3, 0.3)
+    z = torch.randn(32, C, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    r = torch.randn(32, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    y16, y32 = gn_act(z, gn, res32=r, relu=True, want32=True)
+    want = torch.relu(gn(z.float()) + r)
+    assert float((y32 - want).abs().max()) <= 2e-5 * (float(want.abs().max()) + 1)     # fp32 path tolerance
+    assert torch.equal(y16, y32.half())
+    # Dropout2d: whole channels dropped with probability p, survivors scaled by 1/(1-p)
+    y16, _ = gn_act(z, gn, relu=True, drop_p=0.25, seed=3, call_id=9)
+    base, _ = gn_act(z, gn, relu=True)
+    dropped = (y16.float().abs().sum(dim=(2, 3)) == 0) & (base.float().abs().sum(dim=(2, 3)) > 0)
+    frac = float(dropped.float().mean())
+    assert 0.2 < frac < 0.3, frac
+    keep = ~dropped
+    ratio = (y16.float().sum(dim=(2, 3))[keep] / base.float().sum(dim=(2, 3))[keep])
+    assert float((ratio - 1 / 0.75).abs().max()) < 2e-2
