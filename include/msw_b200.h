@@ -100,6 +100,14 @@ typedef struct msw_step_io {
     int32_t *revealed_count;       /* nullable [n]: popcount(revealed) (pre-reset);
                                       revealed_frac = count / (H*W), env.py:165 */
     msw_encode_out enc;            /* observation of the post-(auto-)reset state */
+    /* Built-in synthetic policy for env-only throughput runs: when
+     * rand_mode != 0 the actions are NOT read from actions32/64 (both may be NULL) but drawn
+     * inside the step launch exactly as msw_random_actions(seed=rand_seed, step_index=rand_step,
+     * valid_only = rand_mode == 1) would draw them, and written to actions_out32 (nullable). */
+    int32_t  rand_mode;            /* 0 off, 1 uniformly random unrevealed cell, 2 any cell */
+    uint32_t rand_step;
+    uint64_t rand_seed;
+    int32_t *actions_out32;        /* nullable [n] */
 } msw_step_io;
 
 int msw_version(void);
@@ -168,11 +176,13 @@ int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *m
  * convolutions of the rollout forward (replaces the
  * eager norm/act/dropout/add/cast kernels of cnn_residual.py:17-27, 50-54
  * under the fp16 autocast of train_rl.py:222).  x16: fp16 NHWC [n][HW][C] conv
- * output; statistics and arithmetic in fp32; y16 (fp16 NHWC, the next conv's
+ * output WITHOUT its bias; conv_bias (nullable, fp32 [C]) is added before the
+ * norm; statistics and arithmetic in fp32; y16 (fp16 NHWC, the next conv's
  * input) and/or y32 (fp32 NHWC, the residual stream) are written.  Needs
  * C % 8 == 0 and (C/G) % 8 == 0; drop_p > 0 applies a Dropout2d channel mask
  * keyed by (seed, call_id, sample, channel) and is only allowed without res32. */
-int msw_gn_act(const void *x16, const float *res32, const float *gamma, const float *beta,
+int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
+               const float *gamma, const float *beta,
                void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
                float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
                void *stream);

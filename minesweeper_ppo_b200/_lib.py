@@ -37,6 +37,7 @@ class StepIO(C.Structure):           # msw_step_io
         ("actions32", C.c_void_p), ("actions64", C.c_void_p), ("inject_bits", C.c_void_p),
         ("inject_sel", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("outcome", C.c_void_p),
         ("new_reveals", C.c_void_p), ("step", C.c_void_p), ("revealed_count", C.c_void_p), ("enc", EncodeOut),
+        ("rand_mode", C.c_int32), ("rand_step", C.c_uint32), ("rand_seed", C.c_uint64), ("actions_out32", C.c_void_p),
     ]
 
 
@@ -63,7 +64,7 @@ SIGNATURES = {
     "msw_step_host": (C.c_int, [_P(EnvDesc), _P(State), _P(StepIO), C.c_void_p, _P(HostOut), C.c_int64, C.c_void_p]),
     "msw_masked_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                                     C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "msw_gn_act": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+    "msw_gn_act": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
                              C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]),
 }
 

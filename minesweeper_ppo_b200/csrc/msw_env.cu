@@ -47,6 +47,10 @@ struct EnvParams {
     uint8_t *mask;
     float *labels;
     uint8_t *valid;
+    // built-in synthetic policy (msw_step_io.rand_mode)
+    int rand_mode;
+    uint32_t rk0, rk1, rand_step;
+    int32_t *a_out;
     int vec_mode;                    // 1: 4 cells / lane, 128-bit stores (HW % 4 == 0); 0: scalar
     // per-lane geometry
     uint32_t g_valid[32], g_notcol0[32], g_notlast[32];
@@ -208,6 +212,48 @@ __device__ __forceinline__ void encode_board(const EnvParams &p, long long b, in
     }
 }
 
+// Lemire's multiply-shift with rejection over the four words of one Philox block (shared by the
+// standalone action source and the built-in synthetic policy so both draw the same actions).
+__device__ __forceinline__ uint32_t bounded(const uint32_t (&w)[4], uint32_t range)
+{
+    const uint32_t thresh = (0u - range) % range;
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned long long m = (unsigned long long)w[i] * range;
+        r = (uint32_t)(m >> 32);
+        if ((uint32_t)m >= thresh) break;
+    }
+    return r;
+}
+
+
+// Uniformly random unrevealed cell (or any cell) of the board held in R, warp-parallel; identical
+// to random_actions_kernel for the same (seed, env id, step).
+__device__ __forceinline__ int synth_action(const EnvParams &p, long long b, uint32_t R, int lane, int HW, const Geo &g)
+{
+    const unsigned long long id = (unsigned long long)(p.env_id_base + b);
+    uint32_t w[4];
+    philox4x32_10(p.rk0, p.rk1 ^ 0x41435431u, (uint32_t)id, (uint32_t)(id >> 32), p.rand_step, 0x5eedac71u, w);
+    if (p.rand_mode != 1) return (int)bounded(w, (uint32_t)HW);
+    const uint32_t free_cells = ~R & g.valid;
+    const int c = __popc(free_cells);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return 0;
+    const int k = (int)bounded(w, (uint32_t)total);
+    const unsigned over = __ballot_sync(FULL, incl > k);
+    const int owner = __ffs(over) - 1;
+    int a = 0;
+    if (lane == owner) a = lane * 32 + (int)__fns(free_cells, 0, k - (incl - c) + 1);
+    return __shfl_sync(FULL, a, owner);
+}
+
 // ---------------------------------------------------------------------------
 // The fused env kernel.  MODE_STEP: VecMinesweeper.step (env.py:479-511);
 // MODE_RESET: VecMinesweeper.reset (env.py:468-477); MODE_ENCODE: observation
@@ -234,7 +280,7 @@ __device__ __forceinline__ BoardIn load_board(const EnvParams &p, long long b, i
         in.R = p.revealed[b * wpb + lane];
         if (p.flags) in.F = p.flags[b * wpb + lane];
     }
-    if (MODE == MODE_STEP) {
+    if (MODE == MODE_STEP && !p.rand_mode) {
         if (p.a32) {
             in.a_lo = __ldg(p.a32 + b);
         } else {
@@ -294,7 +340,10 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
         } else {
             // ---- action decode: cell = action % (H*W), Python modulo (env.py:104-107)
             int cell;
-            if (p.a32 || cur.a_hi == (cur.a_lo >> 31)) {
+            if (p.rand_mode) {
+                cell = synth_action(p, b, R, lane, HW, g);
+                if (p.a_out && lane == 0) p.a_out[b] = cell;
+            } else if (p.a32 || cur.a_hi == (cur.a_lo >> 31)) {
                 cell = cur.a_lo % HW;                                     // fits int32
             } else {
                 const long long a = ((long long)cur.a_hi << 32) | (unsigned int)cur.a_lo;
@@ -431,20 +480,6 @@ struct ActParams {
     int32_t *a32;
     long long *a64;
 };
-
-__device__ __forceinline__ uint32_t bounded(const uint32_t (&w)[4], uint32_t range)
-{
-    // Lemire's multiply-shift with rejection over the four words of one Philox block.
-    const uint32_t thresh = (0u - range) % range;
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const unsigned long long m = (unsigned long long)w[i] * range;
-        r = (uint32_t)(m >> 32);
-        if ((uint32_t)m >= thresh) break;
-    }
-    return r;
-}
 
 __global__ void __launch_bounds__(256) random_actions_kernel(const ActParams p)
 {
@@ -662,13 +697,17 @@ static int fill_step(EnvParams &p, const msw_env_desc *desc, const msw_state *st
     int rc = fill_params(p, desc, st, n);
     if (rc) return rc;
     if (!io) return fail(MSW_ERR_NULL, "io is NULL");
-    if ((io->actions32 != nullptr) == (io->actions64 != nullptr))
+    if (io->rand_mode < 0 || io->rand_mode > 2) return fail(MSW_ERR_ARG, "rand_mode must be 0, 1 or 2");
+    if (!io->rand_mode && (io->actions32 != nullptr) == (io->actions64 != nullptr))
         return fail(MSW_ERR_ARG, "exactly one of actions32/actions64 must be set");
     if (!io->reward || !io->done) return fail(MSW_ERR_NULL, "reward/done outputs are required");
     if ((io->inject_sel != nullptr) != (io->inject_bits != nullptr))
         return fail(MSW_ERR_ARG, "inject_bits and inject_sel must be given together");
     p.a32 = io->actions32;
     p.a64 = reinterpret_cast<const long long *>(io->actions64);
+    p.rand_mode = io->rand_mode; p.rand_step = io->rand_step;
+    p.rk0 = (uint32_t)io->rand_seed; p.rk1 = (uint32_t)(io->rand_seed >> 32);
+    p.a_out = io->actions_out32;
     p.inj_bits = io->inject_bits; p.inj_sel = io->inject_sel;
     p.reward = io->reward; p.done = io->done; p.outcome = io->outcome;
     p.new_reveals = io->new_reveals; p.step = io->step; p.rcount = io->revealed_count;

@@ -42,6 +42,7 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
     const int warp = threadIdx.x >> 5;
     const long long col = (long long)blockIdx.x * GAE_COLS + lane;
     const bool in = col < N;
+    constexpr int RPW = GAE_TC / GAE_WARPS;     // rows per warp and chunk (16)
 
     float last = 0.0f;                                          // buffers.py:86
     float next_value = in ? last_values[col] : 0.0f;            // buffers.py:88 (t == T-1)
@@ -51,35 +52,66 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
         const long long t_lo = t_hi > GAE_TC ? t_hi - GAE_TC : 0;
         const int rows = (int)(t_hi - t_lo);
         __syncthreads();
-#pragma unroll 4
-        for (int i = warp; i < rows; i += GAE_WARPS) {
-            const long long k = (t_lo + i) * N + col;
-            s_r[i][lane] = in ? __ldcs(rewards + k) : 0.0f;
-            s_v[i][lane] = in ? __ldcs(values + k) : 0.0f;
-            s_d[i][lane] = in ? __ldcs(dones + k) : (uint8_t)0;
+        // ---- load: every thread issues all of its (up to 3*RPW) loads before the first use, so a
+        // CTA has its whole 36 KB tile in flight at once (the kernel is latency-, not bandwidth-bound)
+        {
+            float r[RPW], v[RPW];
+            uint8_t d[RPW];
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const int i = warp + k * GAE_WARPS;
+                const bool ok = in && i < rows;
+                const long long idx = (t_lo + i) * N + col;
+                r[k] = ok ? __ldcs(rewards + idx) : 0.0f;
+                v[k] = ok ? __ldcs(values + idx) : 0.0f;
+                d[k] = ok ? __ldcs(dones + idx) : (uint8_t)0;
+            }
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const int i = warp + k * GAE_WARPS;
+                s_r[i][lane] = r[k];
+                s_v[i][lane] = v[k];
+                s_d[i][lane] = d[k];
+            }
         }
         __syncthreads();
+        // ---- chain: warp 0, 8 rows per batch read into registers ahead of the dependent arithmetic
         if (warp == 0) {
-#pragma unroll 4
-            for (int i = rows - 1; i >= 0; --i) {
-                const float v = s_v[i][lane];
-                const float nnt = s_d[i][lane] ? 0.0f : 1.0f;
-                const float gv = scaled ? next_value : __fmul_rn(gamma, next_value);
-                scaled = false;
-                const float delta = __fsub_rn(__fadd_rn(s_r[i][lane], __fmul_rn(gv, nnt)), v);
-                last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nnt), last));
-                s_r[i][lane] = last;
-                next_value = v;
+            for (int hi = rows; hi > 0; hi -= 8) {
+                float r[8], v[8], nn[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = hi - 1 - k;
+                    const bool ok = i >= 0;
+                    r[k] = ok ? s_r[ok ? i : 0][lane] : 0.0f;
+                    v[k] = ok ? s_v[ok ? i : 0][lane] : 0.0f;
+                    nn[k] = (ok && s_d[ok ? i : 0][lane]) ? 0.0f : 1.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = hi - 1 - k;
+                    if (i >= 0) {
+                        const float gv = scaled ? next_value : __fmul_rn(gamma, next_value);
+                        scaled = false;
+                        const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(gv, nn[k])), v[k]);
+                        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nn[k]), last));
+                        s_r[i][lane] = last;
+                        next_value = v[k];
+                    }
+                }
             }
         }
         __syncthreads();
         if (in) {
-#pragma unroll 4
-            for (int i = warp; i < rows; i += GAE_WARPS) {
-                const long long k = (t_lo + i) * N + col;
-                const float a = s_r[i][lane];
-                __stcs(adv + k, a);
-                __stcs(ret + k, __fadd_rn(a, s_v[i][lane]));
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const int i = warp + k * GAE_WARPS;
+                if (i < rows) {
+                    const long long idx = (t_lo + i) * N + col;
+                    const float a = s_r[i][lane];
+                    __stcs(adv + idx, a);
+                    __stcs(ret + idx, __fadd_rn(a, s_v[i][lane]));
+                }
             }
         }
     }

@@ -29,6 +29,7 @@ namespace msw {
 
 struct GnParams {
     const __half *x;        // [n][HW][C]
+    const float *cbias;     // nullable [C]: bias of the convolution that produced x, added before the norm
     const float *res;       // nullable [n][HW][C]
     const float *gamma, *beta;   // [C]
     __half *y16;            // nullable [n][HW][C]
@@ -55,10 +56,16 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
     if (tid < 2 * p.G) s_sum[tid] = 0.0f;
     __syncthreads();
 
-    // pass 0: stage the sample, accumulate sums
+    // pass 0: stage the sample, accumulate sums.  The conv bias (a per-channel constant) is folded
+    // in analytically: it shifts the group mean by the mean of the group's biases and each channel
+    // by (bias_c - that mean); the staged tile keeps the raw conv output.
+    float cb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cb[k] = (p.cbias && active) ? p.cbias[j * 8 + k] : 0.0f;
     float acc = 0.0f;
     if (active) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.x) + base;
+        int rows = 0;
         for (int r = r0; r < p.HW; r += p.PPB) {
             const uint4 v = __ldcs(src + r * p.CB + j);
             tile[r * p.CB + j] = v;
@@ -68,11 +75,17 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
                 const float2 f = __half22float2(h[k]);
                 acc += f.x + f.y;
             }
+            ++rows;
         }
-        atomicAdd(&s_sum[g], acc);
+        float bsum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bsum += cb[k];
+        atomicAdd(&s_sum[g], acc + bsum * (float)rows);
     }
     __syncthreads();
     const float mean = s_sum[g] * p.inv_count;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cb[k] -= mean;                 // (x + bias_c) - mean == x + cb[k]
 
     // pass 1: centred second moment (two-pass variance, like torch's RowwiseMoments)
     if (active) {
@@ -83,7 +96,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 f = __half22float2(h[k]);
-                const float a = f.x - mean, b = f.y - mean;
+                const float a = f.x + cb[2 * k], b = f.y + cb[2 * k + 1];
                 acc += a * a + b * b;
             }
         }
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
             const int c = j * 8 + k;
             const float ga = p.gamma[c] * rstd;
             a[k] = ga;
-            b[k] = p.beta[c] - mean * ga;
+            b[k] = fmaf(cb[k], ga, p.beta[c]);                  // beta + (bias_c - mean) * gamma * rstd
             const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
             if (p.drop_p > 0.0f) {
                 // relu(z)*s == relu(z*s) for s >= 0, so the mask/scale folds into the affine when no
@@ -155,7 +168,8 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
 
 }  // namespace msw
 
-extern "C" int msw_gn_act(const void *x16, const float *res32, const float *gamma, const float *beta, void *y16,
+extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *res32, const float *gamma,
+                          const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
                           float drop_p, uint64_t seed, uint64_t call_id, void *stream)
 {
@@ -176,7 +190,7 @@ extern "C" int msw_gn_act(const void *x16, const float *res32, const float *gamm
         configured = 200 * 1024;
     }
     GnParams p;
-    p.x = (const __half *)x16; p.res = res32; p.gamma = gamma; p.beta = beta;
+    p.x = (const __half *)x16; p.cbias = conv_bias; p.res = res32; p.gamma = gamma; p.beta = beta;
     p.y16 = (__half *)y16; p.y32 = y32;
     p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.CB = C / 8; p.PPB = 256 / p.CB;
     p.eps = eps; p.inv_count = 1.0f / (float)((long long)HW * p.cpg);

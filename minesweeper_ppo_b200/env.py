@@ -341,23 +341,40 @@ class VecMinesweeper:
             st["revealed_count"] = torch.empty((n,), dtype=torch.int32, device=dev)
         return st
 
-    def step(self, actions, out: Optional[StepOut] = None, want_infos: bool = True):
+    def step_random(self, step_index: int, valid_only: bool = True, seed: int = 1, out: Optional[StepOut] = None,
+                    actions_out: Optional[torch.Tensor] = None, want_infos: bool = False):
+        """Env-only throughput mode: one launch that draws the synthetic
+        action -- exactly what `random_actions(step_index, valid_only, seed)` returns -- and steps."""
+        if self.api != "torch":
+            raise ValueError("step_random needs api='torch'")
+        return self.step(None, out=out, want_infos=want_infos,
+                         _rand=(1 if valid_only else 2, int(step_index), int(seed), actions_out))
+
+    def step(self, actions, out: Optional[StepOut] = None, want_infos: bool = True, _rand=None):
         """VecMinesweeper.step (env.py:479-511).  Returns (batch, rewards, dones, infos)."""
         if self.api == "numpy":
             return self._step_numpy(actions)
         n, dev = self.num_envs, self.device
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        assert tuple(actions.shape) == (n,)                           # env.py:480
-        if actions.dtype not in (torch.int32, torch.int64):
-            actions = actions.to(torch.int64)
-        actions = actions.to(dev).contiguous()
+        if _rand is None:
+            if not isinstance(actions, torch.Tensor):
+                actions = torch.as_tensor(np.asarray(actions))
+            assert tuple(actions.shape) == (n,)                       # env.py:480
+            if actions.dtype not in (torch.int32, torch.int64):
+                actions = actions.to(torch.int64)
+            actions = actions.to(dev).contiguous()
         o = out if out is not None else self._alloc_encode()
         rewards = o.rewards if o.rewards is not None else torch.empty((n,), dtype=torch.float32, device=dev)
         dones = o.dones if o.dones is not None else torch.empty((n,), dtype=torch.bool, device=dev)
         io = self._io
-        io.actions32 = actions.data_ptr() if actions.dtype == torch.int32 else None
-        io.actions64 = actions.data_ptr() if actions.dtype == torch.int64 else None
+        if _rand is None:
+            io.actions32 = actions.data_ptr() if actions.dtype == torch.int32 else None
+            io.actions64 = actions.data_ptr() if actions.dtype == torch.int64 else None
+            io.rand_mode, io.actions_out32 = 0, None
+        else:
+            mode, step_index, seed, a_out = _rand
+            io.actions32 = io.actions64 = None
+            io.rand_mode, io.rand_step, io.rand_seed = mode, step_index & 0xFFFFFFFF, seed & 0xFFFFFFFFFFFFFFFF
+            io.actions_out32 = self._check(a_out, (n,), torch.int32, "actions_out")
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
         io.reward = self._check(rewards, (n,), torch.float32, "rewards")
@@ -409,6 +426,7 @@ class VecMinesweeper:
             raise ValueError("step_host: actions must be a pinned contiguous int32 [num_envs] CPU tensor")
         io = self._io
         io.actions32, io.actions64 = st["h_actions"].data_ptr(), None
+        io.rand_mode, io.actions_out32 = 0, None
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
         io.reward, io.done = st["h_reward"].data_ptr(), st["h_done"].data_ptr()

@@ -19,24 +19,26 @@ from . import _lib
 from .policy import CNNResidualPolicy
 
 
-def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, res32: Optional[torch.Tensor] = None, relu: bool = True,
+def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[torch.Tensor] = None,
+           res32: Optional[torch.Tensor] = None, relu: bool = True,
            drop_p: float = 0.0, want16: bool = True, want32: bool = False, seed: int = 0, call_id: int = 0
            ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """x16: fp16 [N,C,H,W] in channels_last memory format (conv output).  Returns (y16, y32) with the
-    same logical shape / memory format."""
+    """x16: fp16 [N,C,H,W] in channels_last memory format (conv output, bias NOT applied when
+    `conv_bias` -- fp32 [C] -- is given).  Returns (y16, y32) with the same logical shape / memory format."""
     L = _lib.load()
     if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("gn_act: x must be fp16 channels_last")
     N, C, H, W = x16.shape
     dev = x16.device
     y16 = torch.empty_like(x16, memory_format=torch.channels_last) if want16 else None
-    y32 = (torch.empty((N, C, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+    y32 = (torch.empty((N, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
            if want32 else None)
     if res32 is not None and (res32.dtype != torch.float32 or tuple(res32.shape) != (N, C, H, W)
                               or not res32.is_contiguous(memory_format=torch.channels_last)):
         raise ValueError("gn_act: residual must be fp32 channels_last of the same shape")
     with torch.cuda.device(dev):
-        rc = L.msw_gn_act(x16.data_ptr(), None if res32 is None else res32.data_ptr(), norm.weight.data_ptr(),
+        rc = L.msw_gn_act(x16.data_ptr(), None if conv_bias is None else conv_bias.data_ptr(),
+                          None if res32 is None else res32.data_ptr(), norm.weight.data_ptr(),
                           norm.bias.data_ptr(), None if y16 is None else y16.data_ptr(),
                           None if y32 is None else y32.data_ptr(), N, H * W, C, norm.num_groups, float(norm.eps),
                           int(relu), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFFFFFFFFFF,
@@ -71,18 +73,24 @@ class FusedRolloutForward:
         """Re-cast the (possibly just updated) fp32 parameters to the fp16 copies the convs use."""
         m = self.model
 
-        def conv(c):
-            return (c.weight.detach().to(torch.float16).contiguous(memory_format=torch.channels_last),
-                    None if c.bias is None else c.bias.detach().to(torch.float16))
+        def conv3(c):        # 3x3 conv: fp16 NHWC weight for cuDNN; the bias is folded into msw_gn_act
+            return c.weight.detach().to(torch.float16).contiguous(memory_format=torch.channels_last), c.bias.detach().float()
 
-        def lin(l):
-            return l.weight.detach().to(torch.float16), l.bias.detach().to(torch.float16)
+        def lin(w, b):
+            return w.detach().reshape(w.shape[0], -1).to(torch.float16).contiguous(), b.detach().to(torch.float16)
 
-        self.stem = conv(m.stem[0])
-        self.blocks = [(conv(b.conv1), conv(b.conv2)) for b in m.residual_stack]
-        self.policy = (conv(m.policy_head[0]), conv(m.policy_head[2]))
-        self.mine = (conv(m.mine_head[0]), conv(m.mine_head[2]))
-        self.value = [lin(m.value_head[i]) for i in (2, 4, 6)]
+        self.stem = conv3(m.stem[0])
+        self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
+        # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation;
+        # their first layers share one GEMM, their second layers one block-diagonal GEMM
+        p0, p2, q0, q2 = m.policy_head[0], m.policy_head[2], m.mine_head[0], m.mine_head[2]
+        C = p0.out_channels
+        self.head1 = lin(torch.cat([p0.weight, q0.weight]), torch.cat([p0.bias, q0.bias]))
+        w2 = torch.zeros((2, 2 * C), dtype=p2.weight.dtype, device=p2.weight.device)
+        w2[0, :C] = p2.weight.reshape(-1)
+        w2[1, C:] = q2.weight.reshape(-1)
+        self.head2 = lin(w2, torch.cat([p2.bias, q2.bias]))
+        self.value = [lin(m.value_head[i].weight, m.value_head[i].bias) for i in (2, 4, 6)]
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, return_mine: bool = False):
@@ -90,22 +98,21 @@ class FusedRolloutForward:
         self.calls += 1
         cid = self.calls << 8
         x = obs.to(dtype=torch.float16, memory_format=torch.channels_last)
-        y = F.conv2d(x, *self.stem, padding=1)
-        a16, a32 = gn_act(y, m.stem[1], relu=True, want32=True)
-        for k, (blk, (c1, c2)) in enumerate(zip(m.residual_stack, self.blocks)):
+        a16, a32 = gn_act(F.conv2d(x, self.stem[0], None, padding=1), m.stem[1], conv_bias=self.stem[1], want32=True)
+        for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
-            t16, _ = gn_act(F.conv2d(a16, *c1, padding=1), blk.norm1, relu=True, drop_p=p, seed=self.seed,
+            t16, _ = gn_act(F.conv2d(a16, w1, None, padding=1), blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
                             call_id=cid + k)
-            a16, a32 = gn_act(F.conv2d(t16, *c2, padding=1), blk.norm2, res32=a32, relu=True, want32=True)
-        n, _, h, w = a16.shape
-        logits = F.conv2d(F.relu_(F.conv2d(a16, *self.policy[0])), *self.policy[1])
-        logits = logits.permute(0, 2, 3, 1).reshape(n, h * w)
-        pooled = a32.mean(dim=(2, 3))                              # AdaptiveAvgPool2d(1) in fp32
-        v = pooled.to(torch.float16)
-        v = F.relu_(F.linear(v, *self.value[0]))
+            a16, a32 = gn_act(F.conv2d(t16, w2, None, padding=1), blk.norm2, conv_bias=b2, res32=a32, want32=True)
+        n, c, h, w = a16.shape
+        rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
+        hid = F.relu_(F.linear(rows, *self.head1))                   # [n*h*w, 2C]
+        out = F.linear(hid, *self.head2)                             # [n*h*w, 2]: policy logit, mine logit
+        logits = out[:, 0].reshape(n, h * w)
+        pooled = a32.mean(dim=(2, 3))                                # AdaptiveAvgPool2d(1) in fp32
+        v = F.relu_(F.linear(pooled.to(torch.float16), *self.value[0]))
         v = F.relu_(F.linear(v, *self.value[1]))
         value = F.linear(v, *self.value[2]).squeeze(-1)
         if not return_mine:
             return logits, value
-        mine = F.conv2d(F.relu_(F.conv2d(a16, *self.mine[0])), *self.mine[1])
-        return logits, value, mine
+        return logits, value, out[:, 1].reshape(n, 1, h, w)

@@ -243,3 +243,24 @@ def test_out_buffers_and_bad_arguments(torch_cuda):
         m.VecMinesweeper(4, m.EnvConfig(H=40, W=40, mine_count=10))
     with pytest.raises(NotImplementedError):
         m.VecMinesweeper(4, cfg, late_start_cfg={"prob": 0.5})
+
+
+def test_builtin_synthetic_policy_equals_separate_action_source(torch_cuda):
+    """msw_step with rand_mode draws exactly the action msw_random_actions would have produced."""
+    import minesweeper_ppo_b200 as m
+    torch = torch_cuda
+    for H, W, M in [(16, 16, 40), (16, 30, 99), (9, 9, 10)]:
+        cfg = m.EnvConfig(H=H, W=W, mine_count=M, step_penalty=1e-4)
+        a_env = m.VecMinesweeper(3000, cfg, seed=5, api="torch", aux_maps=True)
+        b_env = m.VecMinesweeper(3000, cfg, seed=5, api="torch", aux_maps=True)
+        a_env.reset(); b_env.reset()
+        acts = torch.empty(3000, dtype=torch.int32, device=a_env.device)
+        for t in range(20):
+            valid_only = t % 4 != 3
+            want = a_env.random_actions(t, valid_only=valid_only, seed=42)
+            ba, ra, da, _ = a_env.step(want)
+            bb, rb, db, _ = b_env.step_random(t, valid_only=valid_only, seed=42, actions_out=acts)
+            assert torch.equal(acts, want), (H, W, t)
+            assert torch.equal(ba["obs"], bb["obs"]) and torch.equal(ba["action_mask"], bb["action_mask"])
+            assert torch.equal(ra, rb) and torch.equal(da, db)
+            assert torch.equal(a_env.mine_labels, b_env.mine_labels)

@@ -40,3 +40,21 @@ with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA, ProfilerActivit
         mcl(xcl, return_mine=True)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
+
+# ---- fused forward (msw_gn_act between cuDNN convs)
+from minesweeper_ppo_b200.fused_forward import FusedRolloutForward
+model.train()
+ff = FusedRolloutForward(model)
+for _ in range(3):
+    ff(x, return_mine=True)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    ff(x, return_mine=True)
+b.record(); torch.cuda.synchronize()
+print(f"fused forward: {a.elapsed_time(b)/5:.2f} ms / forward")
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    ff(x, return_mine=True)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=90))
