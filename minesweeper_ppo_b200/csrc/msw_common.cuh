@@ -131,6 +131,40 @@ __device__ __forceinline__ float4 nib_to_f4(uint32_t nib)
     return v;
 }
 
+// L2 residency control.  The env kernel streams ~690 MB of observations through the 126 MB L2
+// every step; without a hint that stream evicts the few MB of persistent board state, and the
+// next step's state loads queue in HBM behind the writes (ncu: long-scoreboard stalls even on
+// prefetched loads).  State accesses therefore carry an evict_last policy, the observation stream
+// is st.global.cs (evict_first).
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_keep(const uint32_t *p, uint64_t pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int4 ld_keep(const int4 *p, uint64_t pol)
+{
+    int4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_keep(uint32_t *p, uint32_t v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(int4 *p, int4 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // {0,1} nibble -> four bool bytes packed in a u32 (byte k = bit k)
 __device__ __forceinline__ uint32_t nib_to_b4(uint32_t nib)
 {

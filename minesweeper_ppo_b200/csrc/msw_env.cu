@@ -269,16 +269,16 @@ struct BoardIn {
 };
 
 template <int MODE>
-__device__ __forceinline__ BoardIn load_board(const EnvParams &p, long long b, int lane, int wpb)
+__device__ __forceinline__ BoardIn load_board(const EnvParams &p, long long b, int lane, int wpb, uint64_t keep)
 {
     BoardIn in;
     in.M = in.R = in.F = 0u;
     in.a_lo = in.a_hi = 0;
-    in.meta = __ldg(p.meta + b);
+    in.meta = ld_keep(p.meta + b, keep);
     if (MODE != MODE_RESET && lane < wpb) {
-        in.M = p.mines[b * wpb + lane];
-        in.R = p.revealed[b * wpb + lane];
-        if (p.flags) in.F = p.flags[b * wpb + lane];
+        in.M = ld_keep(p.mines + b * wpb + lane, keep);
+        in.R = ld_keep(p.revealed + b * wpb + lane, keep);
+        if (p.flags) in.F = ld_keep(p.flags + b * wpb + lane, keep);
     }
     if (MODE == MODE_STEP && !p.rand_mode) {
         if (p.a32) {
@@ -310,15 +310,16 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
     g.notcol0 = p.g_notcol0[lane];
     g.notlast = p.g_notlast[lane];
     const bool own = lane < wpb;
+    const uint64_t keep = l2_keep_policy();
 
     long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (b >= p.n) return;
-    BoardIn cur = load_board<MODE>(p, b, lane, wpb);
+    BoardIn cur = load_board<MODE>(p, b, lane, wpb, keep);
     while (true) {
         const long long nb = b + total_warps;
         const bool more = nb < p.n;
         BoardIn nxt;
-        if (PF && more) nxt = load_board<MODE>(p, nb, lane, wpb);   // prefetch: consumed next iteration
+        if (PF && more) nxt = load_board<MODE>(p, nb, lane, wpb, keep);   // prefetch: consumed next iteration
 
         uint32_t M = cur.M, R = cur.R, F = cur.F;
         const int4 meta = cur.meta;
@@ -330,11 +331,11 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
             // per-env Generator is never re-seeded either, env.py:49).
             first = 0;
             if (own) {
-                p.mines[b * wpb + lane] = 0u;
-                p.revealed[b * wpb + lane] = 0u;
-                if (p.flags) p.flags[b * wpb + lane] = 0u;
+                st_keep(p.mines + b * wpb + lane, 0u, keep);
+                st_keep(p.revealed + b * wpb + lane, 0u, keep);
+                if (p.flags) st_keep(p.flags + b * wpb + lane, 0u, keep);
             }
-            if (lane == 0) p.meta[b] = make_int4(0, 0, meta.z + 1, 0);
+            if (lane == 0) st_keep(p.meta + b, make_int4(0, 0, meta.z + 1, 0), keep);
         } else if (MODE == MODE_ENCODE) {
             if (first) pl = count_planes<CW>(M, lane, W, g);
         } else {
@@ -407,20 +408,20 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
                 M = 0u; R = 0u; F = 0u;
                 first = 0;
                 pl.c0 = pl.c1 = pl.c2 = pl.c3 = 0u;
-                if (own && p.flags) p.flags[b * wpb + lane] = 0u;
-                if (lane == 0) p.meta[b] = make_int4(0, 0, meta.z + 1, 0);
+                if (own && p.flags) st_keep(p.flags + b * wpb + lane, 0u, keep);
+                if (lane == 0) st_keep(p.meta + b, make_int4(0, 0, meta.z + 1, 0), keep);
             } else if (lane == 0) {
-                p.meta[b] = make_int4(first, step_now, meta.z, newly);
+                st_keep(p.meta + b, make_int4(first, step_now, meta.z, newly), keep);
             }
             if (own) {
-                p.revealed[b * wpb + lane] = R;
-                if (mines_dirty || done) p.mines[b * wpb + lane] = M;
+                st_keep(p.revealed + b * wpb + lane, R, keep);
+                if (mines_dirty || done) st_keep(p.mines + b * wpb + lane, M, keep);
             }
         }
         encode_board<CW, CHW>(p, b, lane, R, M, F, first, pl, g, s_lut);
         if (!more) break;
         if (PF) cur = nxt;
-        else cur = load_board<MODE>(p, nb, lane, wpb);
+        else cur = load_board<MODE>(p, nb, lane, wpb, keep);
         b = nb;
     }
 }
