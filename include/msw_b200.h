@@ -139,6 +139,19 @@ int msw_unpack_state(const msw_env_desc *desc, const msw_state *st, int64_t n,
                      uint8_t *mine, uint8_t *revealed, uint8_t *flags,
                      uint8_t *counts, void *stream);
 
+/* VecMinesweeper._apply_late_start (env.py:416-466) for
+ * freshly reset boards (all of them, or those with sel[i] != 0 -- pass the
+ * `done` output of msw_step): with probability `prob` pre-play random safe
+ * cells until at most target_hidden in [min_hidden, max_hidden] safe cells stay
+ * hidden, retrying up to max_attempts times and leaving the board fresh on
+ * failure.  Randomness: counter-based Philox stream keyed by late_seed (the
+ * reference's shared sequential NumPy generator is not reproducible in
+ * parallel).  Call msw_encode afterwards to observe the resulting boards. */
+int msw_late_start(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                   const uint8_t *sel, uint64_t late_seed, float prob,
+                   int32_t min_hidden, int32_t max_hidden, int32_t max_attempts,
+                   int32_t max_extra_steps, void *stream);
+
 /* Synthetic action source for benchmarks/tests: a
  * uniformly random unrevealed cell per env (valid_only=1; 0 if none) or a
  * uniformly random cell (valid_only=0).  Writes whichever of a32/a64 is

@@ -426,6 +426,141 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Late-start curriculum (env.py:416-466), applied to freshly reset boards:
+// with probability `prob` pre-play random SAFE cells until at most `target_hidden` safe cells stay
+// hidden.  Control flow follows the reference line by line; randomness comes from a counter-based
+// stream (the reference shares ONE sequential NumPy generator over all envs, env.py:397-403, which
+// no parallel implementation can reproduce): draw k of env e is word k%4 of Philox block k/4, key =
+// late-start seed, counter = (env id lo, env id hi, episode index at entry, block); DESIGN.md
+// section 2 specifies the stream, the test-side restatement follows the same specification.
+// ---------------------------------------------------------------------------
+struct LateParams {
+    EnvParams e;
+    const uint8_t *sel;          // nullable [n]: apply only where sel != 0 (the envs a step just reset)
+    uint32_t lk0, lk1;           // late-start seed
+    uint32_t prob24;             // prob * 2^24
+    int min_hidden, max_hidden, max_attempts, max_extra_steps;
+};
+
+struct LateRng {
+    uint32_t k0, k1, c0, c1, c2, idx;
+    uint32_t w[4];
+    __device__ __forceinline__ uint32_t next()
+    {
+        if ((idx & 3u) == 0u) philox4x32_10(k0, k1, c0, c1, c2, idx >> 2, w);
+        const uint32_t i = idx & 3u;
+        ++idx;
+        return i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : w[3];
+    }
+    // Lemire bounded integer with rejection (fresh words on rejection)
+    __device__ __forceinline__ uint32_t below(uint32_t range)
+    {
+        const uint32_t thresh = (0u - range) % range;
+        while (true) {
+            const unsigned long long m = (unsigned long long)next() * range;
+            if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) late_start_kernel(const __grid_constant__ LateParams q)
+{
+    const EnvParams &p = q.e;
+    const int lane = threadIdx.x & 31;
+    const int W = p.W, HW = p.HW, wpb = p.wpb;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= p.n) return;
+    if (q.sel && !q.sel[b]) return;
+    Geo g;
+    g.valid = p.g_valid[lane];
+    g.notcol0 = p.g_notcol0[lane];
+    g.notlast = p.g_notlast[lane];
+    const bool own = lane < wpb;
+    int4 meta = p.meta[b];
+    uint32_t M = 0, R = 0, F = 0;
+    if (own) {
+        M = p.mines[b * wpb + lane];
+        R = p.revealed[b * wpb + lane];
+        if (p.flags) F = p.flags[b * wpb + lane];
+    }
+    int first = meta.x, step_count = meta.y, last_new = meta.w;
+    uint32_t episode = (uint32_t)meta.z;
+    const unsigned long long id = (unsigned long long)(p.env_id_base + b);
+    LateRng rng = {q.lk0, q.lk1, (uint32_t)id, (uint32_t)(id >> 32), episode, 0u, {0u, 0u, 0u, 0u}};
+
+    if ((rng.next() >> 8) >= q.prob24) return;                       // rng.random() >= prob (env.py:422)
+    const int safe_total = HW - p.mine_count;
+    Planes pl = {0u, 0u, 0u, 0u};
+    if (first) pl = count_planes<0>(M, lane, W, g);
+
+    // MinesweeperEnv.step on a cell known to be unrevealed and (after placement) not a mine
+    auto click = [&](int cell) -> bool {
+        const uint32_t startmask = (lane == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
+        if (!first) {
+            M = sample_mines<0, 0>(p, p.env_id_base + b, episode, startmask, lane, g);
+            first = 1;
+            pl = count_planes<0>(M, lane, W, g);
+        }
+        const uint32_t zero = ~(pl.c0 | pl.c1 | pl.c2 | pl.c3) & g.valid;
+        const uint32_t blocked = R | F | M;
+        uint32_t S = startmask & ~F;
+        uint32_t front = S & zero;
+        while (__any_sync(FULL, front)) {
+            const uint32_t D = dilate8<0>(front, lane, W, g) & ~blocked & ~S;
+            S |= D;
+            front = D & zero;
+        }
+        last_new = warp_popc_sum(S);
+        R |= S;
+        step_count += 1;
+        return warp_popc_sum(R) >= safe_total;                        // win (env.py:134-137)
+    };
+    auto fresh = [&]() {                                              // env.reset(), env.py:87-95
+        M = 0u; R = 0u; F = 0u;
+        first = 0; step_count = 0; last_new = 0;
+        episode += 1u;
+        pl.c0 = pl.c1 = pl.c2 = pl.c3 = 0u;
+    };
+
+    bool success = false;
+    for (int attempt = 0; attempt < q.max_attempts && !success; ++attempt) {
+        if (first) fresh();                                           // env.py:437-438
+        bool done = click((int)rng.below((uint32_t)HW));              // env.py:441-442
+        if (done) continue;
+        int target = q.min_hidden + (int)rng.below((uint32_t)(q.max_hidden - q.min_hidden + 1));   // :446
+        target = target < 1 ? 1 : (target > safe_total ? safe_total : target);                     // :447
+        for (int e = 0; e < q.max_extra_steps; ++e) {                 // env.py:449-458
+            if (safe_total - warp_popc_sum(R) <= target) { success = true; break; }
+            const uint32_t cand = ~M & ~R & ~F & g.valid;
+            const int c = __popc(cand);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) break;
+            const int k = (int)rng.below((uint32_t)total);           // rng.choice(safe_candidates)
+            const int owner = __ffs(__ballot_sync(FULL, incl > k)) - 1;
+            int cell = 0;
+            if (lane == owner) cell = lane * 32 + (int)__fns(cand, 0, k - (incl - c) + 1);
+            cell = __shfl_sync(FULL, cell, owner);
+            done = click(cell);
+            if (done) break;
+        }
+        if (!success && !done && safe_total - warp_popc_sum(R) <= target) success = true;   // env.py:460-462
+    }
+    if (!success) fresh();                                            // env.py:465-466
+    if (own) {
+        p.mines[b * wpb + lane] = M;
+        p.revealed[b * wpb + lane] = R;
+        if (p.flags) p.flags[b * wpb + lane] = F;
+    }
+    if (lane == 0) p.meta[b] = make_int4(first, step_count, (int)episode, last_new);
+}
+
 // Expansion of the bitboards into the reference's per-cell arrays for the
 // vec.envs[i] views (env.py:68-71, adjacent_counts per env.py:314-335).
 struct UnpackParams {
@@ -782,6 +917,28 @@ extern "C" int msw_random_actions(const msw_env_desc *desc, const msw_state *st,
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.step_index = step_index;
     p.valid_only = valid_only; p.a32 = a32; p.a64 = reinterpret_cast<long long *>(a64);
     random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+extern "C" int msw_late_start(const msw_env_desc *desc, const msw_state *st, int64_t n, const uint8_t *sel,
+                              uint64_t late_seed, float prob, int32_t min_hidden, int32_t max_hidden,
+                              int32_t max_attempts, int32_t max_extra_steps, void *stream)
+{
+    LateParams q;
+    int rc = fill_params(q.e, desc, st, n);
+    if (rc) return rc;
+    if (!(prob >= 0.0f) || min_hidden < 1 || max_hidden < min_hidden || max_attempts < 1 || max_extra_steps < 1)
+        return fail(MSW_ERR_ARG, "msw_late_start: bad parameters (prob=%f hidden=[%d,%d] attempts=%d extra=%d)",
+                    prob, min_hidden, max_hidden, max_attempts, max_extra_steps);
+    if (n == 0 || prob <= 0.0f) return MSW_OK;
+    q.sel = sel;
+    q.lk0 = (uint32_t)late_seed; q.lk1 = (uint32_t)(late_seed >> 32);
+    const double p24 = (double)prob * 16777216.0;
+    q.prob24 = p24 >= 16777216.0 ? 16777216u : (uint32_t)p24;
+    q.min_hidden = min_hidden; q.max_hidden = max_hidden;
+    q.max_attempts = max_attempts; q.max_extra_steps = max_extra_steps;
+    late_start_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(q);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

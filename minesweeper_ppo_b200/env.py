@@ -155,9 +155,6 @@ class VecMinesweeper:
         assert num_envs > 0                                           # env.py:390
         if api not in ("numpy", "torch"):
             raise ValueError("api must be 'numpy' or 'torch'")
-        if late_start_cfg:
-            raise NotImplementedError(
-                "late_start_cfg (env.py:416-466) is not implemented on device yet (SURVEY 8f, row f3)")
         self._L = _lib.load()                                         # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("VecMinesweeper needs a CUDA device; this package has no CPU fallback")
@@ -198,6 +195,18 @@ class VecMinesweeper:
         self._host_calls: Dict[Any, Any] = {}
         self._pinned_ok: set = set()
         self._staging: Dict[str, torch.Tensor] = {}
+        # late-start curriculum (env.py:397-403, 416-466): parameters normalised as the reference does
+        self._late = None
+        if late_start_cfg:
+            lo = max(1, int(late_start_cfg.get("min_hidden", 5)))
+            hi = max(lo, int(late_start_cfg.get("max_hidden", lo)))
+            ls_seed = (int(late_start_seed) if late_start_seed is not None
+                       else (self.seed * 0x9E3779B97F4A7C15 + 0x5DEECE66D)) & 0xFFFFFFFFFFFFFFFF
+            self._late = (ls_seed, float(late_start_cfg.get("prob", 0.0)), lo, hi,
+                          max(1, int(late_start_cfg.get("max_attempts", 3))),
+                          max(1, int(late_start_cfg.get("max_extra_steps", self.HW))))
+            if self._late[1] <= 0.0:
+                self._late = None
         self.envs = _EnvList(self)
         self.mine_labels: Optional[torch.Tensor] = None               # aux maps of the last reset/step
         self.mine_valid: Optional[torch.Tensor] = None
@@ -248,14 +257,26 @@ class VecMinesweeper:
         enc = _lib.EncodeOut()
         self._fill_encode(enc, o)
         with torch.cuda.device(self.device):
-            _lib.check(self._L.msw_reset(C.byref(self._desc), C.byref(self._state), self.num_envs,
-                                         C.byref(enc), self._stream()), "msw_reset")
+            if self._late is None:
+                _lib.check(self._L.msw_reset(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                             C.byref(enc), self._stream()), "msw_reset")
+            else:                                  # env.py:406-414: reset, late start, then observe
+                _lib.check(self._L.msw_reset(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                             None, self._stream()), "msw_reset")
+                self._apply_late(None, enc)
         self._cache = None
         self._inject = None
         self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
         if self.api == "numpy":
             return {"obs": o.obs.cpu().numpy(), "action_mask": o.action_mask.cpu().numpy()}
         return {"obs": o.obs, "action_mask": o.action_mask}
+
+    def _apply_late(self, sel_ptr: Optional[int], enc: _lib.EncodeOut) -> None:
+        seed, prob, lo, hi, attempts, extra = self._late
+        _lib.check(self._L.msw_late_start(C.byref(self._desc), C.byref(self._state), self.num_envs, sel_ptr, seed,
+                                          prob, lo, hi, attempts, extra, self._stream()), "msw_late_start")
+        _lib.check(self._L.msw_encode(C.byref(self._desc), C.byref(self._state), self.num_envs, C.byref(enc),
+                                      self._stream()), "msw_encode")
 
     # ------------------------------------------------------------------ test / compat hooks
     def inject_layouts(self, mine: Union[np.ndarray, torch.Tensor], sel: Union[np.ndarray, torch.Tensor]) -> None:
@@ -392,8 +413,15 @@ class VecMinesweeper:
             io.outcome = io.new_reveals = io.step = io.revealed_count = None
         self._fill_encode(io.enc, o)
         with torch.cuda.device(dev):
-            _lib.check(self._L.msw_step(C.byref(self._desc), C.byref(self._state), C.byref(io), n, self._stream()),
-                       "msw_step")
+            if self._late is None:
+                _lib.check(self._L.msw_step(C.byref(self._desc), C.byref(self._state), C.byref(io), n,
+                                            self._stream()), "msw_step")
+            else:        # step without observing, late-start the envs that just finished, then observe
+                enc = _lib.EncodeOut(io.enc.obs, io.enc.mask, io.enc.mine_labels, io.enc.mine_valid)
+                io.enc.obs = io.enc.mask = io.enc.mine_labels = io.enc.mine_valid = None
+                _lib.check(self._L.msw_step(C.byref(self._desc), C.byref(self._state), C.byref(io), n,
+                                            self._stream()), "msw_step")
+                self._apply_late(io.done, enc)
         self._inject = None
         self._cache = None
         self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
@@ -472,6 +500,24 @@ class VecMinesweeper:
         n = self.num_envs
         actions = np.asarray(actions)
         assert actions.shape == (n,)                                  # env.py:480
+        if self._late is not None:               # three launches: go through the device-tensor path
+            a = np.mod(actions.astype(np.int64, copy=False), self.HW)
+            self.api = "torch"
+            try:
+                b, r, d, info = self.step(torch.from_numpy(a))
+            finally:
+                self.api = "numpy"
+            dones = d.cpu().numpy()
+            outcome, newr = info["outcome_code"].cpu().numpy(), info["last_new_reveals"].cpu().numpy()
+            step, rc = info["step"].cpu().numpy(), info["revealed_count"].cpu().numpy()
+            infos = {
+                "aux": [{"step": int(step[i]), "last_new_reveals": int(newr[i]),
+                         "revealed_frac": float(int(rc[i]) / max(1, self.HW))} for i in range(n)],
+                "outcome": [_OUTCOME_NAMES[int(outcome[i])] for i in range(n)],
+                "done": [bool(dones[i]) for i in range(n)],
+            }
+            return ({"obs": b["obs"].cpu().numpy(), "action_mask": b["action_mask"].cpu().numpy()},
+                    r.cpu().numpy(), dones, infos)
         pin, _ = self._host_buffers()
         a = actions.astype(np.int64, copy=False)
         # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32

@@ -261,6 +261,24 @@ void orc_vec_reset(const orc_cfg *cfg, int64_t n, orc_state *st,
     orc_parallel_for(n, nthreads, reset_range, &x);
 }
 
+static void encode_range(void *p, int64_t lo, int64_t hi)
+{
+    reset_ctx *x = (reset_ctx *)p;
+    const int H = x->cfg->H, W = x->cfg->W, HW = H * W;
+    orc_state *st = x->st;
+    for (int64_t i = lo; i < hi; ++i)
+        orc_encode(H, W, st->revealed + i * HW, st->flags + i * HW, st->mine + i * HW, st->counts + i * HW,
+                   st->first_click_done[i], x->obs + i * 10 * HW, x->mask + i * HW,
+                   x->labels ? x->labels + i * HW : 0, x->valid ? x->valid + i * HW : 0);
+}
+
+void orc_vec_encode(const orc_cfg *cfg, int64_t n, orc_state *st, float *obs, uint8_t *mask, float *labels,
+                    uint8_t *valid, int nthreads)
+{
+    reset_ctx x = { cfg, st, obs, mask, labels, valid };
+    orc_parallel_for(n, nthreads, encode_range, &x);
+}
+
 typedef struct {
     const orc_cfg *cfg; int64_t env_id_base; const int64_t *actions;
     const uint8_t *inject_mine, *inject_sel; orc_state *st; orc_step_out *out;
@@ -341,6 +359,100 @@ void orc_vec_step(const orc_cfg *cfg, int64_t n, int64_t env_id_base,
 {
     step_ctx x = { cfg, env_id_base, actions, inject_mine, inject_sel, st, out };
     orc_parallel_for(n, nthreads, step_range, &x);
+}
+
+/* ---- late start (env.py:416-466) ---------------------------------------------------------- */
+typedef struct { uint32_t k0, k1, c[3], idx, w[4]; } late_rng;
+
+static uint32_t late_next(late_rng *r)
+{
+    if ((r->idx & 3u) == 0u) {
+        uint32_t ctr[4] = { r->c[0], r->c[1], r->c[2], r->idx >> 2 };
+        orc_philox4x32_10(r->k0, r->k1, ctr, r->w);
+    }
+    return r->w[r->idx++ & 3u];
+}
+
+static uint32_t late_below(late_rng *r, uint32_t range)
+{
+    const uint32_t thresh = (0u - range) % range;
+    for (;;) {
+        const uint64_t m = (uint64_t)late_next(r) * range;
+        if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    }
+}
+
+/* MinesweeperEnv.step (env.py:103-152) on one env of the state arrays; returns done. */
+static int late_click(const orc_cfg *cfg, int64_t env_id, orc_state *st, int64_t i, int cell)
+{
+    const int H = cfg->H, W = cfg->W, HW = H * W;
+    uint8_t *mine = st->mine + i * HW, *rev = st->revealed + i * HW;
+    uint8_t *flg = st->flags + i * HW, *cnt = st->counts + i * HW;
+    int done = 0;
+    st->last_new_reveals[i] = 0;
+    if (!rev[cell]) {
+        if (!st->first_click_done[i]) {
+            orc_place_mines(cfg, env_id, st->episode_idx[i], cell / W, cell % W, mine);
+            orc_adjacent_counts(H, W, mine, cnt);
+            st->first_click_done[i] = 1;
+        }
+        if (mine[cell]) {
+            rev[cell] = 1;
+            done = 1;
+        } else {
+            st->last_new_reveals[i] = orc_flood_fill(H, W, rev, flg, mine, cnt, cell / W, cell % W);
+            int total = 0;
+            for (int k = 0; k < HW; ++k) total += rev[k];
+            if (total >= HW - cfg->mine_count) done = 1;
+        }
+    }
+    st->step_count[i] += 1;
+    return done;
+}
+
+void orc_late_start(const orc_cfg *cfg, int64_t n, int64_t env_id_base, orc_state *st,
+                    const uint8_t *sel, uint64_t late_seed, float prob, int min_hidden,
+                    int max_hidden, int max_attempts, int max_extra_steps)
+{
+    const int HW = cfg->H * cfg->W, safe_total = HW - cfg->mine_count;
+    const double p24d = (double)prob * 16777216.0;
+    const uint32_t prob24 = p24d >= 16777216.0 ? 16777216u : (uint32_t)p24d;
+    if (!(prob > 0.0f)) return;                                         /* env.py:421-423 */
+    for (int64_t i = 0; i < n; ++i) {
+        if (sel && !sel[i]) continue;
+        const uint64_t id = (uint64_t)(env_id_base + i);
+        late_rng r = { (uint32_t)late_seed, (uint32_t)(late_seed >> 32),
+                       { (uint32_t)id, (uint32_t)(id >> 32), st->episode_idx[i] }, 0, {0, 0, 0, 0} };
+        if ((late_next(&r) >> 8) >= prob24) continue;
+        uint8_t *mine = st->mine + i * HW, *rev = st->revealed + i * HW, *flg = st->flags + i * HW;
+        int success = 0;
+        for (int attempt = 0; attempt < max_attempts && !success; ++attempt) {
+            if (st->first_click_done[i]) reset_one(HW, st, i);          /* env.py:437-438 */
+            int done = late_click(cfg, env_id_base + i, st, i, (int)late_below(&r, (uint32_t)HW));
+            if (done) continue;                                         /* env.py:443-444 */
+            int target = min_hidden + (int)late_below(&r, (uint32_t)(max_hidden - min_hidden + 1));
+            if (target < 1) target = 1;
+            if (target > safe_total) target = safe_total;               /* env.py:447 */
+            for (int e = 0; e < max_extra_steps; ++e) {                 /* env.py:449-458 */
+                int revealed = 0, ncand = 0;
+                for (int k = 0; k < HW; ++k) revealed += rev[k];
+                if (safe_total - revealed <= target) { success = 1; break; }
+                for (int k = 0; k < HW; ++k) ncand += (!mine[k] && !rev[k] && !flg[k]);
+                if (ncand == 0) break;
+                int pick = (int)late_below(&r, (uint32_t)ncand), cell = -1;
+                for (int k = 0; k < HW; ++k)
+                    if (!mine[k] && !rev[k] && !flg[k] && pick-- == 0) { cell = k; break; }
+                done = late_click(cfg, env_id_base + i, st, i, cell);
+                if (done) break;
+            }
+            if (!success && !done) {                                    /* env.py:460-462 */
+                int revealed = 0;
+                for (int k = 0; k < HW; ++k) revealed += rev[k];
+                if (safe_total - revealed <= target) success = 1;
+            }
+        }
+        if (!success) reset_one(HW, st, i);                             /* env.py:465-466 */
+    }
 }
 
 /*

@@ -99,12 +99,25 @@ void orc_vec_reset(const orc_cfg *cfg, int64_t n, orc_state *st,
                    float *obs, uint8_t *mask, float *labels, uint8_t *valid,
                    int nthreads);
 
+/* Observation of the current state of every env (env.py:172-196). */
+void orc_vec_encode(const orc_cfg *cfg, int64_t n, orc_state *st, float *obs, uint8_t *mask,
+                    float *labels, uint8_t *valid, int nthreads);
+
 /* env.py:479-511.  inject_sel[i] != 0 => if env i places mines in this step
  * it takes inject_mine[i][H*W] (bytes) instead of sampling. */
 void orc_vec_step(const orc_cfg *cfg, int64_t n, int64_t env_id_base,
                   const int64_t *actions, const uint8_t *inject_mine,
                   const uint8_t *inject_sel, orc_state *st, orc_step_out *out,
                   int nthreads);
+
+/* env.py:416-466 for the envs with sel[i] != 0 (all when sel == NULL), which must be
+ * freshly reset.  Randomness: draw k of env e is word k%4 of Philox block k/4, key =
+ * late_seed, counter = (env id lo, env id hi, episode index at entry, block) -- the
+ * stream specified in DESIGN.md and used by the CUDA path (the reference's shared
+ * sequential NumPy generator cannot be reproduced in parallel). */
+void orc_late_start(const orc_cfg *cfg, int64_t n, int64_t env_id_base, orc_state *st,
+                    const uint8_t *sel, uint64_t late_seed, float prob, int min_hidden,
+                    int max_hidden, int max_attempts, int max_extra_steps);
 
 /* buffers.py:78-94 in IEEE fp32 without contraction. */
 void orc_gae(int64_t T, int64_t N, const float *rewards, const float *values,

@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
         L.orc_vec_reset.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State)] + [C.c_void_p] * 4 + [C.c_int]
         L.orc_vec_step.argtypes = [C.POINTER(_Cfg), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.POINTER(_State), C.POINTER(_StepOut), C.c_int]
+        L.orc_vec_encode.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State)] + [C.c_void_p] * 4 + [C.c_int]
+        L.orc_late_start.argtypes = [C.POINTER(_Cfg), C.c_int64, C.c_int64, C.POINTER(_State), C.c_void_p, C.c_uint64,
+                                     C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_gae.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 2
         _lib = L
     return _lib
@@ -179,7 +182,8 @@ class OracleVecEnv:
     """CPU oracle with the reference VecMinesweeper call shape (env.py:379-517)."""
 
     def __init__(self, num_envs: int, cfg, seed: int = 0, env_id_base: int = 0,
-                 nthreads: int = 1, aux_maps: bool = False, reuse_out: bool = False):
+                 nthreads: int = 1, aux_maps: bool = False, reuse_out: bool = False,
+                 late_start: Optional[Tuple[int, float, int, int, int, int]] = None):
         assert num_envs > 0                                   # env.py:390
         self.cfg, self.num_envs, self.seed = cfg, int(num_envs), int(seed)
         self.H, self.W = int(cfg.H), int(cfg.W)
@@ -201,6 +205,7 @@ class OracleVecEnv:
         self.envs = [_EnvView(self, i) for i in range(n)] if n <= 4096 else None
         self.mine_labels = self.mine_valid = None
         self.reuse_out, self._out = bool(reuse_out), None   # reuse_out: outputs are overwritten each call
+        self.late_start = late_start    # (late_seed, prob, min_hidden, max_hidden, max_attempts, max_extra_steps)
 
     def action_space(self) -> int: return self.HW           # env.py:513-514
     def obs_channels(self) -> int: return OBS_CHANNELS      # env.py:516-517
@@ -220,8 +225,19 @@ class OracleVecEnv:
         obs, mask, lab, val = self._alloc_out()
         lib().orc_vec_reset(C.byref(self._ccfg), self.num_envs, C.byref(self._st),
                             _p(obs), _p(mask), _p(lab), _p(val), self.nthreads)
+        self._late(None, obs, mask, lab, val)
         self.mine_labels, self.mine_valid = lab, (None if val is None else val.view(bool))
         return {"obs": obs, "action_mask": mask.view(bool)}
+
+    def _late(self, sel, obs, mask, lab, val):
+        """env.py:406-414: late start on the envs just reset, then observe them again."""
+        if not self.late_start:
+            return
+        seed, prob, lo, hi, attempts, extra = self.late_start
+        lib().orc_late_start(C.byref(self._ccfg), self.num_envs, self.env_id_base, C.byref(self._st), _p(sel),
+                             int(seed) & 0xFFFFFFFFFFFFFFFF, float(prob), int(lo), int(hi), int(attempts), int(extra))
+        lib().orc_vec_encode(C.byref(self._ccfg), self.num_envs, C.byref(self._st), _p(obs), _p(mask), _p(lab),
+                             _p(val), self.nthreads)
 
     def step(self, actions: np.ndarray, inject_mine: Optional[np.ndarray] = None,
              inject_sel: Optional[np.ndarray] = None, tensor_infos: bool = False
@@ -244,6 +260,7 @@ class OracleVecEnv:
                        _p(rcount), _p(lab), _p(val))
         lib().orc_vec_step(C.byref(self._ccfg), n, self.env_id_base, a64.ctypes.data, _p(inj), _p(sel),
                            C.byref(self._st), C.byref(out), self.nthreads)
+        self._late(done, obs, mask, lab, val)
         self.mine_labels, self.mine_valid = lab, (None if val is None else val.view(bool))
         dones = done.view(bool)
         if tensor_infos:

@@ -305,7 +305,53 @@ def run_rollout_case():
     print(f"rollout: N={N} T={T} dones={int(buf.dones.sum())} placements={len(place_t)}")
 
 
+def run_late_start_stats():
+    """Late-start curriculum (env.py:416-466) draws from ONE sequential generator shared by all envs,
+    so it can only be pinned statistically: summary statistics of the reference after reset() and
+    after 40 random-valid steps, for three configurations."""
+    import json
+    out = {}
+    cases = {
+        "16x16x40_p0.7": (EnvConfig(H=16, W=16, mine_count=40, step_penalty=1e-4),
+                          dict(prob=0.7, min_hidden=5, max_hidden=30, max_attempts=3), 2048),
+        "8x8x10_p1.0": (EnvConfig(), dict(prob=1.0, min_hidden=2, max_hidden=6), 4096),
+        "4x4x3_p0.9": (EnvConfig(H=4, W=4, mine_count=3), dict(prob=0.9, min_hidden=1, max_hidden=2, max_attempts=2,
+                                                                  max_extra_steps=6), 4096),
+    }
+    for name, (cfg, ls, N) in cases.items():
+        HW = cfg.H * cfg.W
+        safe = HW - cfg.mine_count
+        vec = VecMinesweeper(N, cfg, seed=11, late_start_cfg=ls, late_start_seed=12)
+        b = vec.reset()
+
+        def stats():
+            f = np.array([e.first_click_done for e in vec.envs])
+            hid = np.array([safe - int((e.revealed & ~e.mine_mask).sum()) for e in vec.envs])
+            sc = np.array([e.step_count for e in vec.envs])
+            return {"frac_started": float(f.mean()), "mean_safe_hidden_started": float(hid[f].mean()) if f.any() else 0.0,
+                    "max_safe_hidden_started": int(hid[f].max()) if f.any() else 0,
+                    "mean_step_count_started": float(sc[f].mean()) if f.any() else 0.0}
+
+        after_reset = stats()
+        rng = np.random.default_rng(1)
+        mask = b["action_mask"]
+        wins = losses = 0
+        for t in range(40):
+            s_ = rng.random(mask.shape); s_[~mask] = -1
+            b, r, d, info = vec.step(s_.argmax(1).astype(np.int32))
+            mask = b["action_mask"]
+            wins += sum(o == "win" for o in info["outcome"]); losses += sum(o == "loss" for o in info["outcome"])
+        out[name] = {"cfg": dict(H=cfg.H, W=cfg.W, mine_count=cfg.mine_count), "late_start": ls, "N": N,
+                     "after_reset": after_reset, "after_40_steps": stats(),
+                     "win_rate_random_play": wins / max(1, wins + losses)}
+        print("late_start", name, out[name]["after_reset"], out[name]["win_rate_random_play"])
+    json.dump(out, open(os.path.join(OUT, "late_start_stats.json"), "w"), indent=1)
+
+
 def main():
+    if "--late-only" in sys.argv:
+        run_late_start_stats()
+        return
     std = dict(guarantee_safe_neighborhood=True, step_penalty=1e-4)
     run_env_case("16x16x40_valid", EnvConfig(H=16, W=16, mine_count=40, **std), 48, 96, "valid", 0)
     run_env_case("16x16x40_any", EnvConfig(H=16, W=16, mine_count=40, **std), 48, 96, "any", 1)
@@ -322,6 +368,7 @@ def main():
     run_floodfill_case()
     run_gae_cases()
     run_rollout_case()
+    run_late_start_stats()
 
 
 if __name__ == "__main__":

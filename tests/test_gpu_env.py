@@ -241,8 +241,6 @@ def test_out_buffers_and_bad_arguments(torch_cuda):
                                 action_mask=nxt.action_mask))
     with pytest.raises(ValueError):
         m.VecMinesweeper(4, m.EnvConfig(H=40, W=40, mine_count=10))
-    with pytest.raises(NotImplementedError):
-        m.VecMinesweeper(4, cfg, late_start_cfg={"prob": 0.5})
 
 
 def test_builtin_synthetic_policy_equals_separate_action_source(torch_cuda):
