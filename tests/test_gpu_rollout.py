@@ -147,3 +147,22 @@ def test_fused_forward_matches_autocast_module(C, blocks, HW):
     keep = ~dropped
     ratio = (y16.float().sum(dim=(2, 3))[keep] / base.float().sum(dim=(2, 3))[keep])
     assert float((ratio - 1 / 0.75).abs().max()) < 2e-2
+
+
+def test_eval_compat_c1():
+    """BASELINE.json configs[0]: eval yaml env (16x16x40), 64 envs, 256 episodes, random-init medium
+    policy, greedy argmax through the NumPy API and the vec.envs[i] views.  An untrained greedy
+    policy loses almost immediately: the survey measured win_rate 0.0 / avg_steps 1.95 on the
+    reference; layouts differ (different sampler), so only the regime is
+    asserted."""
+    import torch
+    import minesweeper_ppo_b200 as m
+    from minesweeper_ppo_b200.evaluate import evaluate_vec
+    torch.manual_seed(0)
+    model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
+                          model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).cuda()
+    cfg = m.EnvConfig(H=16, W=16, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    r = evaluate_vec(model, cfg, episodes=256, seed=0, num_envs=64)
+    assert r["episodes"] == 256 and r["invalid_rate"] == 0.0
+    assert r["win_rate"] <= 0.05 and 1.0 <= r["avg_steps"] <= 12.0
+    assert 0.0 < r["avg_progress"] < 1.0 and 0.3 < r["belief_auroc"] < 0.7      # untrained belief head ~ chance
