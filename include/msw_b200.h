@@ -152,6 +152,18 @@ int msw_late_start(const msw_env_desc *desc, const msw_state *st, int64_t n,
                    int32_t min_hidden, int32_t max_hidden, int32_t max_attempts,
                    int32_t max_extra_steps, void *stream);
 
+/* Compact replay + fused minibatch gather, replacing the
+ * obs / action_mask / mine_labels / mine_valid index gathers of
+ * RolloutBuffer.get_minibatches (buffers.py:96-116): transitions are stored as
+ * bitboard snapshots (snap_mines / snap_revealed / nullable snap_flags
+ * [rows_in][wpb], snap_first [rows_in]) and row j of the minibatch is re-encoded
+ * from snapshot idx[j] straight into `out` (m rows).  Bit-identical to gathering
+ * rows of a dense buffer. */
+int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_mines,
+                      const uint32_t *snap_revealed, const uint32_t *snap_flags,
+                      const uint8_t *snap_first, int64_t rows_in, const int64_t *idx,
+                      int64_t m, const msw_encode_out *out, void *stream);
+
 /* Synthetic action source for benchmarks/tests: a
  * uniformly random unrevealed cell per env (valid_only=1; 0 if none) or a
  * uniformly random cell (valid_only=0).  Writes whichever of a32/a64 is

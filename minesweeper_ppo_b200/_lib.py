@@ -68,6 +68,8 @@ SIGNATURES = {
                              C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]),
     "msw_late_start": (C.c_int, [_P(EnvDesc), _P(State), C.c_int64, C.c_void_p, C.c_uint64, C.c_float, C.c_int32,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "msw_gather_encode": (C.c_int, [_P(EnvDesc)] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int64,
+                                    _P(EncodeOut), C.c_void_p]),
 }
 
 _lib = None

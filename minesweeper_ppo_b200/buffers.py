@@ -17,8 +17,10 @@ from typing import Dict, Iterator, Optional, Tuple
 import numpy as np
 import torch
 
+import ctypes as C
+
 from . import _lib
-from .env import StepOut
+from .env import StepOut, VecMinesweeper
 
 
 class RolloutBuffer:
@@ -144,3 +146,87 @@ class RolloutBuffer:
         for start in range(0, total, batch_size):
             rows = order[start: start + batch_size]
             yield type("Batch", (), {name: tensor[rows] for name, tensor in fields})
+
+
+class CompactRolloutBuffer(RolloutBuffer):
+    """RolloutBuffer that stores each transition's OBSERVATION as the bitboards it was encoded from
+    (SURVEY section 8 row f2): mines + revealed (+ flags) + first_click_done = 65 B per transition
+    at 16x16 instead of 11.8 KB of obs / action_mask / mine_labels / mine_valid, and re-encodes the
+    rows of a minibatch on the fly (msw_gather_encode) inside `get_minibatches`.  Batches are
+    bit-identical to the dense buffer's for the same permutation; the dense `obs` / `action_mask` /
+    `mine_*` attributes do not exist."""
+
+    def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool = False):
+        n, dev = vec.num_envs, vec.device
+        self.num_envs, self.steps, self.device = n, int(steps), dev
+        self.vec, self.aux_maps = vec, bool(aux_maps)
+        B = n * self.steps
+        self.snap_mines = torch.zeros((B, vec.wpb), dtype=torch.int32, device=dev)
+        self.snap_revealed = torch.zeros((B, vec.wpb), dtype=torch.int32, device=dev)
+        self.snap_flags: Optional[torch.Tensor] = None
+        self.snap_first = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        self.actions = torch.zeros((B,), dtype=torch.long, device=dev)
+        self.logp = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((B,), dtype=torch.bool, device=dev)
+        self.values = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.advantages = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.returns = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.obs = self.action_mask = self.mine_labels = self.mine_valid = None
+        self._t = 0
+
+    def snapshot(self, t: int) -> None:
+        """Record the env's CURRENT state as the observation of slot t (call right after the
+        reset / step whose observation slot t holds)."""
+        n = self.num_envs
+        rows = slice(t * n, (t + 1) * n)
+        st = self.vec.state_tensors
+        self.snap_mines[rows] = st["mines"]
+        self.snap_revealed[rows] = st["revealed"]
+        self.snap_first[rows] = st["meta"][:, 0].to(torch.uint8)
+        if st["flags"] is not None:
+            if self.snap_flags is None:
+                self.snap_flags = torch.zeros_like(self.snap_mines)
+            self.snap_flags[rows] = st["flags"]
+
+    def slot(self, t: int) -> StepOut:
+        raise RuntimeError("CompactRolloutBuffer has no dense observation slots; use snapshot(t)")
+
+    def add(self, *a, **k) -> None:
+        raise RuntimeError("CompactRolloutBuffer is filled by RolloutCollector(compact=True)")
+
+    def gather_obs(self, rows: torch.Tensor) -> StepOut:
+        """Dense obs / mask (/ aux maps) of the given transition rows, re-encoded on device."""
+        L = _lib.load()
+        v = self.vec
+        m = int(rows.numel())
+        rows = rows.to(device=self.device, dtype=torch.int64).contiguous()
+        out = StepOut(
+            obs=torch.empty((m, v.obs_channels(), v.H, v.W), dtype=torch.float32, device=self.device),
+            action_mask=torch.empty((m, v.HW), dtype=torch.bool, device=self.device),
+            mine_labels=torch.empty((m, v.H, v.W), dtype=torch.float32, device=self.device) if self.aux_maps else None,
+            mine_valid=torch.empty((m, v.H, v.W), dtype=torch.bool, device=self.device) if self.aux_maps else None)
+        enc = _lib.EncodeOut(out.obs.data_ptr(), out.action_mask.data_ptr(),
+                             None if out.mine_labels is None else out.mine_labels.data_ptr(),
+                             None if out.mine_valid is None else out.mine_valid.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = L.msw_gather_encode(C.byref(v._desc), self.snap_mines.data_ptr(), self.snap_revealed.data_ptr(),
+                                     None if self.snap_flags is None else self.snap_flags.data_ptr(),
+                                     self.snap_first.data_ptr(), self.snap_mines.shape[0], rows.data_ptr(), m,
+                                     C.byref(enc), torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "msw_gather_encode")
+        return out
+
+    def get_minibatches(self, batch_size: int) -> Iterator[Dict[str, torch.Tensor]]:
+        total = self.num_envs * self.steps
+        order = torch.randperm(total, device=self.device)
+        small = [("actions", self.actions), ("old_logp", self.logp), ("rewards", self.rewards), ("dones", self.dones),
+                 ("values", self.values), ("advantages", self.advantages), ("returns", self.returns)]
+        for start in range(0, total, batch_size):
+            rows = order[start: start + batch_size]
+            dense = self.gather_obs(rows)
+            batch = {"obs": dense.obs, "action_mask": dense.action_mask}
+            batch.update({name: tensor[rows] for name, tensor in small})
+            if self.aux_maps:
+                batch["mine_labels"], batch["mine_valid"] = dense.mine_labels, dense.mine_valid
+            yield type("Batch", (), batch)

@@ -561,6 +561,55 @@ __global__ void __launch_bounds__(128) late_start_kernel(const __grid_constant__
     if (lane == 0) p.meta[b] = make_int4(first, step_count, (int)episode, last_new);
 }
 
+// ---------------------------------------------------------------------------
+// Compact replay: a transition is stored as the bitboards that generated
+// its observation (mines + revealed [+ flags] + first_click_done: 65 B at 16x16 instead of the
+// 11.8 KB of obs + mask + aux maps), and RolloutBuffer.get_minibatches' randperm gather
+// (buffers.py:96-116) becomes this kernel: row j of the minibatch is re-encoded from snapshot
+// idx[j] straight into the minibatch tensors.  Same encoder as the step kernel, so the result is
+// bit-identical to gathering rows of a dense buffer.
+// ---------------------------------------------------------------------------
+struct GatherParams {
+    EnvParams e;                     // geometry + destination pointers (obs/mask/labels/valid), n = rows out
+    const uint32_t *s_mines, *s_revealed, *s_flags;   // [rows_in][wpb] (s_flags nullable)
+    const uint8_t *s_first;          // [rows_in]
+    const long long *idx;            // [n] source row of each output row
+    long long rows_in;
+};
+
+template <int CW, int CHW>
+__global__ void __launch_bounds__(256) gather_encode_kernel(const __grid_constant__ GatherParams q)
+{
+    __shared__ float4 s_lut[16];
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = nib_to_f4(threadIdx.x);
+    __syncthreads();
+    const EnvParams &p = q.e;
+    const int lane = threadIdx.x & 31;
+    const int W = CW ? CW : p.W;
+    const int HW = CHW ? CHW : p.HW;
+    const int wpb = (HW + 31) >> 5;
+    const long long warps_per_block = blockDim.x >> 5;
+    const long long total_warps = (long long)gridDim.x * warps_per_block;
+    Geo g;
+    g.valid = p.g_valid[lane];
+    g.notcol0 = p.g_notcol0[lane];
+    g.notlast = p.g_notlast[lane];
+    for (long long j = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); j < p.n; j += total_warps) {
+        long long src = q.idx[j];
+        if (src < 0 || src >= q.rows_in) src = 0;               // host validates; never fault on a bad index
+        uint32_t M = 0, R = 0, F = 0;
+        if (lane < wpb) {
+            M = __ldg(q.s_mines + src * wpb + lane);
+            R = __ldg(q.s_revealed + src * wpb + lane);
+            if (q.s_flags) F = __ldg(q.s_flags + src * wpb + lane);
+        }
+        const int first = q.s_first[src] != 0;
+        Planes pl = {0u, 0u, 0u, 0u};
+        if (first) pl = count_planes<CW>(M, lane, W, g);
+        encode_board<CW, CHW>(p, j, lane, R, M, F, first, pl, g, s_lut);
+    }
+}
+
 // Expansion of the bitboards into the reference's per-cell arrays for the
 // vec.envs[i] views (env.py:68-71, adjacent_counts per env.py:314-335).
 struct UnpackParams {
@@ -939,6 +988,35 @@ extern "C" int msw_late_start(const msw_env_desc *desc, const msw_state *st, int
     q.min_hidden = min_hidden; q.max_hidden = max_hidden;
     q.max_attempts = max_attempts; q.max_extra_steps = max_extra_steps;
     late_start_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(q);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+extern "C" int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_mines, const uint32_t *snap_revealed,
+                                 const uint32_t *snap_flags, const uint8_t *snap_first, int64_t rows_in,
+                                 const int64_t *idx, int64_t m, const msw_encode_out *out, void *stream)
+{
+    if (!snap_mines || !snap_revealed || !snap_first || !idx) return fail(MSW_ERR_NULL, "msw_gather_encode: NULL pointer");
+    if (rows_in < 1) return fail(MSW_ERR_BAD_SHAPE, "msw_gather_encode: rows_in=%lld", (long long)rows_in);
+    GatherParams q;
+    msw_state fake = { const_cast<uint32_t *>(snap_mines), const_cast<uint32_t *>(snap_revealed),
+                       const_cast<uint32_t *>(snap_flags), reinterpret_cast<int32_t *>(const_cast<uint32_t *>(snap_mines)) };
+    if (((uintptr_t)snap_mines & 15u) != 0) return fail(MSW_ERR_ALIGN, "msw_gather_encode: snapshots must be 16-byte aligned");
+    int rc = fill_params(q.e, desc, &fake, m);
+    if (rc) return rc;
+    if ((rc = set_encode_out(q.e, out, true))) return rc;
+    q.e.flags = const_cast<uint32_t *>(snap_flags);           // encoder consults flags only when present
+    q.s_mines = snap_mines; q.s_revealed = snap_revealed; q.s_flags = snap_flags; q.s_first = snap_first;
+    q.idx = reinterpret_cast<const long long *>(idx); q.rows_in = rows_in;
+    if (m == 0) return MSW_OK;
+    long long blocks = (m + 7) / 8;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (q.e.W == 16 && q.e.HW == 256)
+        gather_encode_kernel<16, 256><<<(unsigned)blocks, 256, 0, st>>>(q);
+    else
+        gather_encode_kernel<0, 0><<<(unsigned)blocks, 256, 0, st>>>(q);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

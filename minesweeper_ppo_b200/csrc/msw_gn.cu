@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
     uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);                       // [HW][CB] chunks of 8 halves
     float *s_sum = reinterpret_cast<float *>(smem_raw + (size_t)p.HW * p.C * 2);   // [G]
     float *s_sq = s_sum + p.G;
+    float *s_part = s_sq + p.G;                                                   // [256] per-thread partials
 
     const int tid = threadIdx.x;
     const int j = tid % p.CB, r0 = tid / p.CB;
@@ -53,8 +54,20 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
     const int g = (j * 8) / p.cpg;
     const long long n = blockIdx.x;
     const long long base = n * (long long)p.HW * p.CB;                       // in uint4 chunks
-    if (tid < 2 * p.G) s_sum[tid] = 0.0f;
-    __syncthreads();
+    // Group totals are formed from the per-thread partials in a FIXED order (no float atomics), so
+    // the kernel is bitwise reproducible run to run, like the eager GroupNorm it replaces.
+    auto group_total = [&](float mine, float *dst) {
+        s_part[tid] = active ? mine : 0.0f;
+        __syncthreads();
+        if (tid < p.G) {
+            const int j0 = tid * (p.cpg / 8), j1 = j0 + p.cpg / 8;
+            float t = 0.0f;
+            for (int r = 0; r < p.PPB; ++r)
+                for (int jj = j0; jj < j1; ++jj) t += s_part[r * p.CB + jj];
+            dst[tid] = t;
+        }
+        __syncthreads();
+    };
 
     // pass 0: stage the sample, accumulate sums.  The conv bias (a per-channel constant) is folded
     // in analytically: it shifts the group mean by the mean of the group's biases and each channel
@@ -80,16 +93,16 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
         float bsum = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) bsum += cb[k];
-        atomicAdd(&s_sum[g], acc + bsum * (float)rows);
+        acc += bsum * (float)rows;
     }
-    __syncthreads();
+    group_total(acc, s_sum);
     const float mean = s_sum[g] * p.inv_count;
 #pragma unroll
     for (int k = 0; k < 8; ++k) cb[k] -= mean;                 // (x + bias_c) - mean == x + cb[k]
 
     // pass 1: centred second moment (two-pass variance, like torch's RowwiseMoments)
+    acc = 0.0f;
     if (active) {
-        acc = 0.0f;
         for (int r = r0; r < p.HW; r += p.PPB) {
             const uint4 v = tile[r * p.CB + j];
             const __half2 *h = reinterpret_cast<const __half2 *>(&v);
@@ -100,9 +113,8 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
                 acc += a * a + b * b;
             }
         }
-        atomicAdd(&s_sq[g], acc);
     }
-    __syncthreads();
+    group_total(acc, s_sq);
     if (!active) return;
     const float rstd = rsqrtf(s_sq[g] * p.inv_count + p.eps);
 
@@ -182,7 +194,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     if ((((uintptr_t)x16 | (uintptr_t)res32 | (uintptr_t)y16 | (uintptr_t)y32) & 15u) != 0)
         return fail(MSW_ERR_ALIGN, "msw_gn_act: tensors must be 16-byte aligned");
     if (n == 0) return MSW_OK;
-    const size_t smem = (size_t)HW * C * 2 + 2 * (size_t)G * sizeof(float);
+    const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 256) * sizeof(float);
     if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: sample of %zu bytes does not fit shared memory", smem);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .buffers import RolloutBuffer
+from .buffers import CompactRolloutBuffer, RolloutBuffer
 from .env import StepOut, VecMinesweeper
 from .fused_forward import FusedRolloutForward
 
@@ -62,14 +62,20 @@ def masked_sample(logits: torch.Tensor, mask: torch.Tensor, *, seed: int, step_i
 class RolloutCollector:
     """Reusable collector: owns the buffer and scratch tensors so repeated rollouts allocate nothing."""
 
-    def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool, sample_seed: int = 0, fused: bool = True):
+    def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool, sample_seed: int = 0, fused: bool = True,
+                 compact: bool = False):
         if vec.api != "torch":
             raise ValueError("RolloutCollector needs VecMinesweeper(api='torch')")
         self.vec, self.steps, self.aux_maps = vec, int(steps), bool(aux_maps)
         N, dev = vec.num_envs, vec.device
         vec.aux_maps = self.aux_maps
-        self.buffer = RolloutBuffer(N, self.steps, (vec.obs_channels(), vec.H, vec.W), vec.action_space(), dev,
-                                    aux_maps=self.aux_maps)
+        self.compact = bool(compact)
+        if self.compact:      # SURVEY 8 f2: transitions stored as bitboards, two dense scratch slots for the forward
+            self.buffer = CompactRolloutBuffer(vec, self.steps, aux_maps=self.aux_maps)
+            self._scratch = [vec._alloc_encode(), vec._alloc_encode()]
+        else:
+            self.buffer = RolloutBuffer(N, self.steps, (vec.obs_channels(), vec.H, vec.W), vec.action_space(), dev,
+                                        aux_maps=self.aux_maps)
         self.last = vec._alloc_encode()                       # observation after the final step (bootstrap)
         self.actions32 = torch.empty((N,), dtype=torch.int32, device=dev)
         self.sample_seed = int(sample_seed)
@@ -81,7 +87,12 @@ class RolloutCollector:
     def collect(self, model: nn.Module, autocast: bool = True) -> Tuple[RolloutBuffer, Dict]:
         vec, buf, T = self.vec, self.buffer, self.steps
         N, dev = vec.num_envs, vec.device
-        vec.reset(out=buf.slot(0))                            # train_rl.py:163: every rollout starts fresh
+        def obs_slot(t):      # where the observation of time t lives (dense buffer slot or scratch)
+            return buf.slot(t) if not self.compact else self._scratch[t & 1]
+
+        vec.reset(out=obs_slot(0))                            # train_rl.py:163: every rollout starts fresh
+        if self.compact:
+            buf.snapshot(0)
         buf._t = 0
         ctx = (lambda: torch.autocast(device_type="cuda", dtype=torch.float16)) if autocast else nullcontext
         base_step = self.rollouts_done * (T + 1)
@@ -92,7 +103,7 @@ class RolloutCollector:
             self._fused_fwd.refresh()                         # weights may have been updated since
             fwd, ctx = self._fused_fwd, nullcontext
         for t in range(T):
-            cur = buf.slot(t)
+            cur = obs_slot(t)
             rows = slice(t * N, (t + 1) * N)
             with ctx():                                       # train_rl.py:222-227
                 if self.aux_maps:
@@ -103,10 +114,12 @@ class RolloutCollector:
                           row_id_base=vec._desc.env_id_base, actions64=buf.actions[rows],
                           actions32=self.actions32, logp=buf.logp[rows])
             buf.values[rows] = values.float()                 # train_rl.py:256
-            nxt = buf.slot(t + 1) if t + 1 < T else self.last
-            vec.step(self.actions32, out=StepOut(obs=nxt.obs, action_mask=nxt.action_mask, rewards=cur.rewards,
-                                                 dones=cur.dones, mine_labels=nxt.mine_labels,
+            nxt = obs_slot(t + 1) if t + 1 < T else self.last
+            vec.step(self.actions32, out=StepOut(obs=nxt.obs, action_mask=nxt.action_mask, rewards=buf.rewards[rows],
+                                                 dones=buf.dones[rows], mine_labels=nxt.mine_labels,
                                                  mine_valid=nxt.mine_valid), want_infos=False)
+            if self.compact and t + 1 < T:
+                buf.snapshot(t + 1)
         buf._t = T
         with ctx():                                           # bootstrap value, train_rl.py:267-277
             if self.aux_maps:

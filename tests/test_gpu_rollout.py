@@ -122,7 +122,10 @@ def test_fused_forward_matches_autocast_module(C, blocks, HW):
     x = (torch.rand(64, 10, H, W, device="cuda") < 0.3).float()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         ref = net(x, return_mine=True)
-    got = FusedRolloutForward(net)(x, return_mine=True)
+    ff = FusedRolloutForward(net)
+    got = ff(x, return_mine=True)
+    again = ff(x, return_mine=True)
+    assert all(torch.equal(u, v) for u, v in zip(got, again)), "fused forward must be bitwise reproducible"
     for a, b, name in zip(got, ref, ("logits", "value", "mine")):
         assert a.shape == b.shape and a.dtype == torch.float16, name
         err = float((a.float() - b.float()).abs().max())
@@ -166,3 +169,54 @@ def test_eval_compat_c1():
     assert r["episodes"] == 256 and r["invalid_rate"] == 0.0
     assert r["win_rate"] <= 0.05 and 1.0 <= r["avg_steps"] <= 12.0
     assert 0.0 < r["avg_progress"] < 1.0 and 0.3 < r["belief_auroc"] < 0.7      # untrained belief head ~ chance
+
+
+@pytest.mark.parametrize("H,W,M", [(16, 16, 40), (16, 30, 99), (9, 9, 10)])
+def test_compact_replay_gather_equals_dense_buffer(H, W, M):
+    """re-encoding minibatch rows from bitboard snapshots == gathering dense buffer rows."""
+    import torch
+    import minesweeper_ppo_b200 as m
+    N, T = 512, 20
+    cfg = m.EnvConfig(H=H, W=W, mine_count=M, step_penalty=1e-4)
+    vec = m.VecMinesweeper(N, cfg, seed=4, api="torch", aux_maps=True)
+    dense = m.RolloutBuffer(N, T, (10, H, W), H * W, vec.device, aux_maps=True)
+    comp = m.CompactRolloutBuffer(vec, T, aux_maps=True)
+    scratch = vec._alloc_encode()
+    vec.reset(out=dense.slot(0)); comp.snapshot(0)
+    for t in range(T):
+        nxt = dense.slot(t + 1) if t + 1 < T else scratch
+        cur = dense.slot(t)
+        vec.step_random(t, out=m.StepOut(obs=nxt.obs, action_mask=nxt.action_mask, rewards=cur.rewards, dones=cur.dones,
+                                         mine_labels=nxt.mine_labels, mine_valid=nxt.mine_valid))
+        if t + 1 < T:
+            comp.snapshot(t + 1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rows = torch.randperm(N * T, device="cuda", generator=g)[:3000]
+    got = comp.gather_obs(rows)
+    assert torch.equal(got.obs, dense.obs[rows]) and torch.equal(got.action_mask, dense.action_mask[rows])
+    assert torch.equal(got.mine_labels, dense.mine_labels[rows]) and torch.equal(got.mine_valid, dense.mine_valid[rows])
+    assert float(got.obs.sum()) > 0
+    batches = list(comp.get_minibatches(4096))
+    assert sum(b.obs.shape[0] for b in batches) == N * T and batches[0].obs.shape[1:] == (10, H, W)
+
+
+def test_compact_collector_matches_dense_collector():
+    import torch
+    import minesweeper_ppo_b200 as m
+    cfg = m.EnvConfig(H=16, W=16, mine_count=40, step_penalty=1e-4)
+    torch.manual_seed(0)
+    model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
+                          model_cfg=dict(stem_channels=32, blocks=2, dropout=0.0, value_hidden=64)).cuda().eval()
+    outs = []
+    for compact in (False, True):
+        vec = m.VecMinesweeper(256, cfg, seed=9, api="torch")
+        col = m.RolloutCollector(vec, 16, aux_maps=True, sample_seed=5, compact=compact)
+        buf, aux = col.collect(model)
+        outs.append((buf, aux))
+    (d, da), (c, ca) = outs
+    for f in ("actions", "logp", "rewards", "dones", "values"):
+        assert torch.equal(getattr(d, f), getattr(c, f)), f
+    assert torch.equal(da["last_values"], ca["last_values"])
+    rows = torch.arange(0, 256 * 16, 7, device="cuda")
+    got = c.gather_obs(rows)
+    assert torch.equal(got.obs, d.obs[rows]) and torch.equal(got.mine_valid, d.mine_valid[rows])
