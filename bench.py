@@ -36,6 +36,7 @@ ENVS_PER_GPU = 65536
 # obs 40*HW + mask HW + reward 4 + done 1 + action 4
 BYTES_PER_STEP = 41 * H * W + 9          # 10,505 B
 WORKLOAD = "C2"
+VALID_ONLY = True
 
 
 def set_workload(name: str, envs):
@@ -215,7 +216,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     actions_log = torch.empty((Wm + Ke + 1, N), dtype=torch.int32, device=dev)
     vec.reset(out=slots[0])
     for t in range(Wm):
-        vec.step_random(t, out=slots[t % ring], actions_out=actions_log[t])
+        vec.step_random(t, valid_only=VALID_ONLY, out=slots[t % ring], actions_out=actions_log[t])
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -226,7 +227,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     for t in range(K):
         a = actions_log[Wm + min(t, Ke)]       # first Ke action sets are kept for the e2e replay
         kev[t][0].record()
-        vec.step_random(Wm + t, out=slots[t % ring], actions_out=a)      # synthetic policy + step: one launch
+        vec.step_random(Wm + t, valid_only=VALID_ONLY, out=slots[t % ring], actions_out=a)   # policy + step: one launch
         kev[t][1].record()
     ev1.record()
     barrier()
@@ -295,8 +296,9 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         "dtype": "u32", "data": "synthetic",
         "config": {
             "workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_per_gpu": N, "envs_total": total_envs,
-            "actions": "uniform random valid cell per env per step, drawn inside the step launch "
-                       "(msw_step rand_mode=1; identical to msw_random_actions)",
+            "actions": ("uniform random valid cell" if VALID_ONLY else "uniform random cell (series B, no-op clicks included)")
+                       + " per env per step, drawn inside the step launch (msw_step rand_mode; identical to "
+                         "msw_random_actions)",
             "auto_reset": True, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
             "l2": f"each step writes {BYTES_PER_STEP * N / 1e6:.0f} MB of obs/mask into a ring of {ring} slots "
                   "(>> 126 MB L2), no explicit flush",
@@ -468,6 +470,9 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--workload", default="C2", choices=["C2", "C4"])
+    ap.add_argument("--actions", default="valid", choices=["valid", "any"],
+                    help="BASELINE.md C2 series A (uniform random unrevealed cell, the bench line) or "
+                         "series B (uniform random cell, includes no-op clicks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value and roofline only")
     ap.add_argument("--no-gae", action="store_true")
@@ -475,6 +480,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     set_workload(args.workload, args.envs)
+    global VALID_ONLY
+    VALID_ONLY = args.actions == "valid"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

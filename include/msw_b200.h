@@ -191,11 +191,13 @@ int msw_gae(const float *rewards, const float *values, const uint8_t *dones,
  * fill value (-1e9 for f32, -1e4 for half types), soft-maxed in fp32, one
  * action per row is drawn by inverse CDF with a Philox uniform keyed by
  * (seed, row_id_base + row, step_index), and log_prob(action) is returned.
+ * `epoch` (nullable device uint32) is added to the high word of step_index when
+ * the kernel runs, so a captured CUDA graph draws fresh numbers on each replay.
  * Writes whichever of actions64 / actions32 / logp is non-NULL. */
 int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *mask,
                       int64_t n, int32_t A, uint64_t seed, uint64_t step_index,
-                      int64_t row_id_base, int64_t *actions64, int32_t *actions32,
-                      float *logp, void *stream);
+                      const uint32_t *epoch, int64_t row_id_base, int64_t *actions64,
+                      int32_t *actions32, float *logp, void *stream);
 
 /* Fused GroupNorm + (fp32 residual add) + ReLU + Dropout2d between the cuDNN
  * convolutions of the rollout forward (replaces the
@@ -205,12 +207,13 @@ int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *m
  * norm; statistics and arithmetic in fp32; y16 (fp16 NHWC, the next conv's
  * input) and/or y32 (fp32 NHWC, the residual stream) are written.  Needs
  * C % 8 == 0 and (C/G) % 8 == 0; drop_p > 0 applies a Dropout2d channel mask
- * keyed by (seed, call_id, sample, channel) and is only allowed without res32. */
+ * keyed by (seed, call_id [+ *epoch in the high word], sample, channel) and is
+ * only allowed without res32. */
 int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
                const float *gamma, const float *beta,
                void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
                float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
-               void *stream);
+               const uint32_t *epoch, void *stream);
 
 /* Host-buffer form of msw_step for callers that keep the reference's NumPy
  * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):

@@ -38,6 +38,7 @@ struct GnParams {
     float eps, inv_count, drop_p, drop_scale;
     int relu;
     uint32_t k0, k1, call_lo, call_hi;
+    const uint32_t *epoch;  // nullable device counter added to call_hi (fresh dropout masks per graph replay)
 };
 
 __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
     {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (p.drop_p > 0.0f)
-            philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo, p.call_hi, w);
+            philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo,
+                          p.call_hi + (p.epoch ? *p.epoch : 0u), w);
         const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
 extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *res32, const float *gamma,
                           const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
-                          float drop_p, uint64_t seed, uint64_t call_id, void *stream)
+                          float drop_p, uint64_t seed, uint64_t call_id, const uint32_t *epoch, void *stream)
 {
     using namespace msw;
     if (!x16 || !gamma || !beta || (!y16 && !y32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
@@ -210,6 +212,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.relu = relu;
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
     p.call_lo = (uint32_t)call_id; p.call_hi = (uint32_t)(call_id >> 32);
+    p.epoch = epoch;
     if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: n too large");
     gn_act_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
     MSW_CUDA_TRY(cudaGetLastError());

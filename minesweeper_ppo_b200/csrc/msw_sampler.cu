@@ -38,7 +38,7 @@ template <typename T, int MAXC>
 __global__ void __launch_bounds__(128)
 masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ mask, long long n, int A,
                      float neg_inf_in, uint32_t k0, uint32_t k1, uint32_t step_lo, uint32_t step_hi,
-                     long long row_id_base, long long *__restrict__ a64, int32_t *__restrict__ a32,
+                     const uint32_t *__restrict__ epoch, long long row_id_base, long long *__restrict__ a64, int32_t *__restrict__ a32,
                      float *__restrict__ logp)
 {
     const int lane = threadIdx.x & 31;
@@ -84,7 +84,9 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
 
     const unsigned long long rid = (unsigned long long)(row_id_base + row);
     uint32_t w[4];
-    philox4x32_10(k0, k1 ^ 0x53414d50u, (uint32_t)rid, (uint32_t)(rid >> 32), step_lo, step_hi, w);
+    // `epoch` (device counter, nullable) lets a captured CUDA graph draw fresh numbers on every replay
+    const uint32_t hi = step_hi + (epoch ? *epoch : 0u);
+    philox4x32_10(k0, k1 ^ 0x53414d50u, (uint32_t)rid, (uint32_t)(rid >> 32), step_lo, hi, w);
     const float u = ((float)(w[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
     const float target = u * total;
 
@@ -122,7 +124,8 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
 }  // namespace msw
 
 extern "C" int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *mask, int64_t n,
-                                 int32_t A, uint64_t seed, uint64_t step_index, int64_t row_id_base,
+                                 int32_t A, uint64_t seed, uint64_t step_index, const uint32_t *epoch,
+                                 int64_t row_id_base,
                                  int64_t *actions64, int32_t *actions32, float *logp, void *stream)
 {
     using namespace msw;
@@ -140,13 +143,13 @@ extern "C" int msw_masked_sample(const void *logits, int32_t logits_dtype, const
     do {                                                                                                        \
         if (chunk <= 8)                                                                                         \
             masked_sample_kernel<T, 8><<<grid, 128, 0, st>>>((const T *)logits, mask, n, A, NEG, k0, k1, s0, s1, \
-                                                             row_id_base, a64, actions32, logp);               \
+                                                             epoch, row_id_base, a64, actions32, logp);               \
         else if (chunk <= 16)                                                                                   \
             masked_sample_kernel<T, 16><<<grid, 128, 0, st>>>((const T *)logits, mask, n, A, NEG, k0, k1, s0,   \
-                                                              s1, row_id_base, a64, actions32, logp);          \
+                                                              s1, epoch, row_id_base, a64, actions32, logp);          \
         else                                                                                                    \
             masked_sample_kernel<T, 32><<<grid, 128, 0, st>>>((const T *)logits, mask, n, A, NEG, k0, k1, s0,   \
-                                                              s1, row_id_base, a64, actions32, logp);          \
+                                                              s1, epoch, row_id_base, a64, actions32, logp);          \
     } while (0)
     switch (logits_dtype) {                       // fill constants of train_rl.py:229-232
     case 0: MSW_LAUNCH_SAMPLER(float, -1e9f); break;

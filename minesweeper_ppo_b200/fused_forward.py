@@ -21,8 +21,8 @@ from .policy import CNNResidualPolicy
 
 def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[torch.Tensor] = None,
            res32: Optional[torch.Tensor] = None, relu: bool = True,
-           drop_p: float = 0.0, want16: bool = True, want32: bool = False, seed: int = 0, call_id: int = 0
-           ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+           drop_p: float = 0.0, want16: bool = True, want32: bool = False, seed: int = 0, call_id: int = 0,
+           epoch: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x16: fp16 [N,C,H,W] in channels_last memory format (conv output, bias NOT applied when
     `conv_bias` -- fp32 [C] -- is given).  Returns (y16, y32) with the same logical shape / memory format."""
     L = _lib.load()
@@ -42,7 +42,7 @@ def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[t
                           norm.bias.data_ptr(), None if y16 is None else y16.data_ptr(),
                           None if y32 is None else y32.data_ptr(), N, H * W, C, norm.num_groups, float(norm.eps),
                           int(relu), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFFFFFFFFFF,
-                          torch.cuda.current_stream(dev).cuda_stream)
+                          None if epoch is None else epoch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "msw_gn_act")
     return y16, y32
 
@@ -58,7 +58,8 @@ class FusedRolloutForward:
         if C % 8 or (C // G) % 8:
             raise ValueError(f"fused forward needs C % 8 == 0 and (C/G) % 8 == 0, got C={C} G={G}")
         self.model, self.seed, self.calls = model, int(seed), 0
-        self._w: List[torch.Tensor] = []
+        self.epoch: Optional[torch.Tensor] = None     # device uint32 counter mixed into the dropout RNG (graph replays)
+        self._w: List = []
         self.refresh()
 
     @staticmethod
@@ -70,27 +71,47 @@ class FusedRolloutForward:
 
     @torch.no_grad()
     def refresh(self) -> None:
-        """Re-cast the (possibly just updated) fp32 parameters to the fp16 copies the convs use."""
+        """Re-cast the (possibly just updated) fp32 parameters into the fp16 copies the convs use.
+        The copies are allocated once and updated IN PLACE, so their addresses are stable and the
+        whole forward -- including this refresh -- can live inside a captured CUDA graph."""
         m = self.model
-
-        def conv3(c):        # 3x3 conv: fp16 NHWC weight for cuDNN; the bias is folded into msw_gn_act
-            return c.weight.detach().to(torch.float16).contiguous(memory_format=torch.channels_last), c.bias.detach().float()
-
-        def lin(w, b):
-            return w.detach().reshape(w.shape[0], -1).to(torch.float16).contiguous(), b.detach().to(torch.float16)
-
-        self.stem = conv3(m.stem[0])
-        self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
-        # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation;
-        # their first layers share one GEMM, their second layers one block-diagonal GEMM
         p0, p2, q0, q2 = m.policy_head[0], m.policy_head[2], m.mine_head[0], m.mine_head[2]
         C = p0.out_channels
-        self.head1 = lin(torch.cat([p0.weight, q0.weight]), torch.cat([p0.bias, q0.bias]))
-        w2 = torch.zeros((2, 2 * C), dtype=p2.weight.dtype, device=p2.weight.device)
-        w2[0, :C] = p2.weight.reshape(-1)
-        w2[1, C:] = q2.weight.reshape(-1)
-        self.head2 = lin(w2, torch.cat([p2.bias, q2.bias]))
-        self.value = [lin(m.value_head[i].weight, m.value_head[i].bias) for i in (2, 4, 6)]
+        if not self._w:
+            def conv3(c):    # 3x3 conv: fp16 NHWC weight for cuDNN; the bias is folded into msw_gn_act
+                return (torch.empty_like(c.weight, dtype=torch.float16, memory_format=torch.channels_last),
+                        torch.empty_like(c.bias, dtype=torch.float32))
+
+            def lin(out_f, in_f, dev):
+                return (torch.empty((out_f, in_f), dtype=torch.float16, device=dev),
+                        torch.empty((out_f,), dtype=torch.float16, device=dev))
+
+            dev = p0.weight.device
+            self.stem = conv3(m.stem[0])
+            self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
+            # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation;
+            # their first layers share one GEMM, their second layers one block-diagonal GEMM
+            self.head1 = lin(2 * C, C, dev)
+            self.head2 = lin(2, 2 * C, dev)
+            self.head2[0].zero_()
+            self.value = [lin(m.value_head[i].out_features, m.value_head[i].in_features, dev) for i in (2, 4, 6)]
+            self._w = [self.stem]
+
+        def put3(dst, c):
+            dst[0].copy_(c.weight)
+            dst[1].copy_(c.bias)
+
+        put3(self.stem, m.stem[0])
+        for (d1, d2), b in zip(self.blocks, m.residual_stack):
+            put3(d1, b.conv1)
+            put3(d2, b.conv2)
+        self.head1[0][:C].copy_(p0.weight.reshape(C, C)); self.head1[0][C:].copy_(q0.weight.reshape(C, C))
+        self.head1[1][:C].copy_(p0.bias); self.head1[1][C:].copy_(q0.bias)
+        self.head2[0][0, :C].copy_(p2.weight.reshape(-1)); self.head2[0][1, C:].copy_(q2.weight.reshape(-1))
+        self.head2[1][0:1].copy_(p2.bias); self.head2[1][1:2].copy_(q2.bias)
+        for dst, i in zip(self.value, (2, 4, 6)):
+            dst[0].copy_(m.value_head[i].weight)
+            dst[1].copy_(m.value_head[i].bias)
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, return_mine: bool = False):
@@ -102,7 +123,7 @@ class FusedRolloutForward:
         for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
             t16, _ = gn_act(F.conv2d(a16, w1, None, padding=1), blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
-                            call_id=cid + k)
+                            call_id=cid + k, epoch=self.epoch)
             a16, a32 = gn_act(F.conv2d(t16, w2, None, padding=1), blk.norm2, conv_bias=b2, res32=a32, want32=True)
         n, c, h, w = a16.shape
         rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy

@@ -29,7 +29,8 @@ _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 def masked_sample(logits: torch.Tensor, mask: torch.Tensor, *, seed: int, step_index: int, row_id_base: int = 0,
                   actions64: Optional[torch.Tensor] = None, actions32: Optional[torch.Tensor] = None,
-                  logp: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  logp: Optional[torch.Tensor] = None, epoch: Optional[torch.Tensor] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Masked Categorical sample + log_prob in one launch (replaces train_rl.py:229-235, :239)."""
     L = _lib.load()
     if logits.device.type != "cuda":
@@ -53,6 +54,7 @@ def masked_sample(logits: torch.Tensor, mask: torch.Tensor, *, seed: int, step_i
     with torch.cuda.device(dev):
         rc = L.msw_masked_sample(logits.data_ptr(), _DTYPE_CODE[logits.dtype], mask.data_ptr(), n, A,
                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index) & 0xFFFFFFFFFFFFFFFF,
+                                 None if epoch is None else epoch.data_ptr(),
                                  int(row_id_base), actions64.data_ptr(), actions32.data_ptr(), logp.data_ptr(),
                                  torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "msw_masked_sample")
@@ -63,7 +65,7 @@ class RolloutCollector:
     """Reusable collector: owns the buffer and scratch tensors so repeated rollouts allocate nothing."""
 
     def __init__(self, vec: VecMinesweeper, steps: int, aux_maps: bool, sample_seed: int = 0, fused: bool = True,
-                 compact: bool = False):
+                 compact: bool = False, graph: bool = False):
         if vec.api != "torch":
             raise ValueError("RolloutCollector needs VecMinesweeper(api='torch')")
         self.vec, self.steps, self.aux_maps = vec, int(steps), bool(aux_maps)
@@ -82,9 +84,43 @@ class RolloutCollector:
         self.rollouts_done = 0
         self.fused = bool(fused)          # use FusedRolloutForward when the model supports it
         self._fused_fwd = None
+        # graph=True: the WHOLE rollout (reset, T x (forward, sample, step), bootstrap forward, weight
+        # refresh) is captured once into a CUDA graph and replayed -- one launch per rollout instead of
+        # ~35 per step, which is what matters when N is small and every kernel is launch-bound.  A
+        # device-side epoch counter, bumped inside the graph, keeps sampler / dropout draws fresh.
+        self.use_graph = bool(graph)
+        self._graph = None
+        self._graph_aux = None
+        self._epoch = torch.zeros(1, dtype=torch.int32, device=dev) if self.use_graph else None
+
+    @staticmethod
+    def can_graph(model: nn.Module) -> bool:
+        """graph=True needs the fused forward, i.e. a CNNResidualPolicy with 8 | channels-per-group."""
+        return FusedRolloutForward.supports(model)
 
     @torch.no_grad()
     def collect(self, model: nn.Module, autocast: bool = True) -> Tuple[RolloutBuffer, Dict]:
+        if not self.use_graph:
+            return self._collect(model, autocast)
+        if not (self.fused and autocast and FusedRolloutForward.supports(model)):
+            raise ValueError("graph=True needs the fused forward (CNNResidualPolicy, fused=True, CUDA autocast)")
+        if self._graph is None or self._fused_fwd.model is not model:
+            side = torch.cuda.Stream(device=self.vec.device)
+            side.wait_stream(torch.cuda.current_stream(self.vec.device))
+            with torch.cuda.stream(side):                       # warm-up outside capture (cuDNN plans, lazy inits)
+                self._collect(model, autocast)
+            torch.cuda.current_stream(self.vec.device).wait_stream(side)
+            torch.cuda.synchronize(self.vec.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._epoch.add_(1)
+                _, aux = self._collect(model, autocast)
+            self._graph, self._graph_aux = g, aux
+        self._graph.replay()
+        self.buffer._t = self.steps
+        return self.buffer, dict(self._graph_aux)
+
+    def _collect(self, model: nn.Module, autocast: bool = True) -> Tuple[RolloutBuffer, Dict]:
         vec, buf, T = self.vec, self.buffer, self.steps
         N, dev = vec.num_envs, vec.device
         def obs_slot(t):      # where the observation of time t lives (dense buffer slot or scratch)
@@ -100,6 +136,7 @@ class RolloutCollector:
         if self.fused and autocast and FusedRolloutForward.supports(model):
             if self._fused_fwd is None or self._fused_fwd.model is not model:
                 self._fused_fwd = FusedRolloutForward(model, seed=self.sample_seed)
+                self._fused_fwd.epoch = self._epoch
             self._fused_fwd.refresh()                         # weights may have been updated since
             fwd, ctx = self._fused_fwd, nullcontext
         for t in range(T):
@@ -112,7 +149,7 @@ class RolloutCollector:
                     logits, values = fwd(cur.obs)
             masked_sample(logits, cur.action_mask, seed=self.sample_seed, step_index=base_step + t,
                           row_id_base=vec._desc.env_id_base, actions64=buf.actions[rows],
-                          actions32=self.actions32, logp=buf.logp[rows])
+                          actions32=self.actions32, logp=buf.logp[rows], epoch=self._epoch)
             buf.values[rows] = values.float()                 # train_rl.py:256
             nxt = obs_slot(t + 1) if t + 1 < T else self.last
             vec.step(self.actions32, out=StepOut(obs=nxt.obs, action_mask=nxt.action_mask, rewards=buf.rewards[rows],

@@ -212,7 +212,7 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
                      aux_mine_weight=cfg.aux_mine_weight, aux_mine_calib_weight=cfg.aux_mine_calib_weight,
                      max_grad_norm=cfg.max_grad_norm, beta_l2=float((extras.get("training") or {}).get("beta_l2", 0.0)))
     need_aux = pcfg.aux_mine_weight > 0 or pcfg.aux_mine_calib_weight > 0
-    collector = RolloutCollector(vec, T, aux_maps=need_aux, sample_seed=seed)
+    collector = RolloutCollector(vec, T, aux_maps=need_aux, sample_seed=seed, graph=RolloutCollector.can_graph(model))
     grads = FlatGradAllReduce(model)
     mb = (n_local * T) // cfg.mini_batches
 

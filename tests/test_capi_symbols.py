@@ -25,6 +25,21 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
 
 
+def test_binding_arity_matches_header():
+    """ctypes silently accepts extra arguments and truncates them to 32 bits, so a binding that is
+    one argtype short corrupts the last pointer (the stream).  Count the parameters of every
+    prototype in the header and compare with the binding."""
+    from minesweeper_ppo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "msw_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(msw_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_host_side_calls_without_device(lib):
     assert lib.msw_version() == 1
     assert lib.msw_words_per_board(16, 16) == 8 and lib.msw_words_per_board(16, 30) == 15

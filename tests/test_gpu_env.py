@@ -262,3 +262,43 @@ def test_builtin_synthetic_policy_equals_separate_action_source(torch_cuda):
             assert torch.equal(ba["obs"], bb["obs"]) and torch.equal(ba["action_mask"], bb["action_mask"])
             assert torch.equal(ra, rb) and torch.equal(da, db)
             assert torch.equal(a_env.mine_labels, b_env.mine_labels)
+
+
+def test_random_board_shapes_against_oracle(torch_cuda, oracle):
+    """Sweep of random (H, W, mines, safe-neighbourhood) combinations -- including W in {1, 31, 32},
+    planes that are not 16-byte multiples (scalar encoder) and dense boards (complement sampling) --
+    each stepped against the oracle, everything compared bit for bit."""
+    import os
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 12), (12, 1), (2, 2), (3, 31), (31, 3), (32, 32), (7, 32), (32, 7), (5, 5), (10, 10), (24, 30)]
+    while len(shapes) < 26:
+        W = int(rng.integers(1, 33)); H = int(rng.integers(1, 1024 // W + 1))
+        shapes.append((min(H, 40), W))
+    for k, (H, W) in enumerate(shapes):
+        HW = H * W
+        if HW < 2:
+            continue
+        M = int(rng.integers(0, HW))                 # 0 .. HW-1, so sparse, dense and mine-free boards all occur
+        cfg = NS(H=H, W=W, mine_count=M, guarantee_safe_neighborhood=bool(k % 3), win_reward=1.0,
+                 loss_reward=-1.0, step_penalty=1e-4)
+        N = 257
+        gpu = P.CudaAdapter(cfg, N, seed=k, env_id_base=k * 1000)
+        cpu = oracle.OracleVecEnv(N, cfg, seed=k, env_id_base=k * 1000, aux_maps=True, nthreads=os.cpu_count() or 1)
+        o, mk = gpu.reset(); b = cpu.reset()
+        P.assert_bits_equal(o, b["obs"], f"{H}x{W}x{M} reset obs")
+        for t in range(8):
+            a = gpu.v.random_actions(t, valid_only=bool(t % 2), seed=k)
+            g = gpu.step(a)
+            bc, r, d, info = cpu.step(a.cpu().numpy().astype(np.int64), tensor_infos=True)
+            tag = f"{H}x{W}x{M} t={t}"
+            P.assert_bits_equal(g["obs"], bc["obs"], tag + " obs")
+            P.assert_bits_equal(g["mask"], bc["action_mask"], tag + " mask")
+            P.assert_bits_equal(g["rewards"], r, tag + " rewards")
+            P.assert_bits_equal(g["dones"], d, tag + " dones")
+            P.assert_bits_equal(g["outcome"], info["outcome_code"], tag + " outcome")
+            P.assert_bits_equal(g["new_reveals"], info["last_new_reveals"], tag + " new")
+            P.assert_bits_equal(g["labels"], cpu.mine_labels, tag + " labels")
+            P.assert_bits_equal(g["valid"], cpu.mine_valid, tag + " valid")
+        s = gpu.state()
+        P.assert_bits_equal(s["mine"], cpu.mine.astype(bool), f"{H}x{W}x{M} mines")
+        P.assert_bits_equal(s["counts"], cpu.counts, f"{H}x{W}x{M} counts")

@@ -220,3 +220,46 @@ def test_compact_collector_matches_dense_collector():
     rows = torch.arange(0, 256 * 16, 7, device="cuda")
     got = c.gather_obs(rows)
     assert torch.equal(got.obs, d.obs[rows]) and torch.equal(got.mine_valid, d.mine_valid[rows])
+
+
+def test_graph_captured_rollout(oracle):
+    """RolloutCollector(graph=True): the whole rollout is one CUDA-graph replay.  Replays must draw
+    fresh actions (device-side epoch counter) and stay consistent with the env semantics: replaying
+    the recorded actions through the oracle reproduces every env-written buffer field bit for bit."""
+    import os
+    import torch
+    import minesweeper_ppo_b200 as m
+    torch.manual_seed(0)
+    N, T = 128, 16
+    cfg = m.EnvConfig(H=16, W=16, mine_count=40, step_penalty=1e-4)
+    vec = m.VecMinesweeper(N, cfg, seed=2, api="torch")
+    model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
+                          model_cfg=dict(stem_channels=32, blocks=2, dropout=0.05, value_hidden=64)).cuda()
+    col = m.RolloutCollector(vec, T, aux_maps=True, sample_seed=3, graph=True)
+    b1, _ = col.collect(model)
+    torch.cuda.synchronize()
+    a1, v1 = b1.actions.clone(), b1.values.clone()
+    ep = vec.state_tensors["meta"][:, 2].cpu().numpy().astype(np.uint32)
+    with torch.no_grad():                                   # weights change between rollouts (in-place refresh)
+        for p_ in model.parameters():
+            p_.mul_(1.01)
+    b2, aux = col.collect(model)
+    torch.cuda.synchronize()
+    assert not torch.equal(a1, b2.actions) and not torch.equal(v1, b2.values)
+    c = lambda t_: t_.cpu().numpy()
+    ref = oracle.OracleVecEnv(N, cfg, seed=2, nthreads=os.cpu_count() or 1, aux_maps=True)
+    ref.episode_idx[:] = ep
+    b = ref.reset()
+    obs, mask, lab = b["obs"], b["action_mask"], ref.mine_labels
+    acts = c(b2.actions).reshape(T, N)
+    for t in range(T):
+        s = slice(t * N, (t + 1) * N)
+        P.assert_bits_equal(c(b2.obs[s]), obs, f"slot {t} obs")
+        P.assert_bits_equal(c(b2.action_mask[s]), mask, f"slot {t} mask")
+        P.assert_bits_equal(c(b2.mine_labels[s]), lab, f"slot {t} labels")
+        assert mask[np.arange(N), acts[t]].all()
+        bb, r, d, _ = ref.step(acts[t], tensor_infos=True)
+        P.assert_bits_equal(c(b2.rewards[s]), r, f"slot {t} rewards")
+        P.assert_bits_equal(c(b2.dones[s]), d, f"slot {t} dones")
+        obs, mask, lab = bb["obs"], bb["action_mask"], ref.mine_labels
+    assert aux["last_values"].shape == (N,)
