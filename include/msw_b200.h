@@ -213,7 +213,23 @@ int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
                const float *gamma, const float *beta,
                void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
                float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
-               const uint32_t *epoch, void *stream);
+               const uint32_t *epoch, float *save_mean, float *save_rstd,
+               uint8_t *save_mask, void *stream);
+
+/* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
+ * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and
+ * Dropout2d) come from the forward call (all three nullable there, given
+ * together).  g16 / g32 are the upstream gradients of y16 / y32 (either may be
+ * NULL).  Writes dx16 (gradient of the conv output, fp16), dres32 (nullable,
+ * gradient of res32) and per-sample partial sums [n][C] of the gamma / beta /
+ * conv-bias gradients, which the caller reduces over n (fixed order, no float
+ * atomics). */
+int msw_gn_act_bwd(const void *x16, const float *conv_bias, const float *gamma,
+                   const float *mean, const float *rstd, const uint8_t *mask,
+                   const void *g16, const float *g32, void *dx16, float *dres32,
+                   float *part_dgamma, float *part_dbeta, float *part_dbias,
+                   int64_t n, int32_t HW, int32_t C, int32_t G, float drop_p,
+                   void *stream);
 
 /* Host-buffer form of msw_step for callers that keep the reference's NumPy
  * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):

@@ -39,6 +39,9 @@ struct GnParams {
     int relu;
     uint32_t k0, k1, call_lo, call_hi;
     const uint32_t *epoch;  // nullable device counter added to call_hi (fresh dropout masks per graph replay)
+    // training forward: what msw_gn_act_bwd needs (all nullable)
+    float *save_mean, *save_rstd;   // [n][G] statistics of (x + conv_bias)
+    uint8_t *save_mask;             // [n][HW][C/8]: bit k of a byte = output channel 8j+k is "on" (ReLU active, not dropped)
 };
 
 __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
@@ -116,11 +119,16 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
         }
     }
     group_total(acc, s_sq);
+    if (p.save_mean && tid < p.G) {
+        p.save_mean[n * p.G + tid] = s_sum[tid] * p.inv_count;
+        p.save_rstd[n * p.G + tid] = rsqrtf(s_sq[tid] * p.inv_count + p.eps);
+    }
     if (!active) return;
     const float rstd = rsqrtf(s_sq[g] * p.inv_count + p.eps);
 
     // per-channel affine folded with the statistics, and the Dropout2d channel mask
     float a[8], b[8];
+    uint32_t kept = 0xFFu;                                    // channels that survive Dropout2d
     {
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (p.drop_p > 0.0f)
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
                 // relu(z)*s == relu(z*s) for s >= 0, so the mask/scale folds into the affine when no
                 // residual is added (Dropout2d follows ReLU only on that path, cnn_residual.py:20-21)
                 const float s = (u16 < thresh) ? 0.0f : p.drop_scale;
+                if (u16 < thresh) kept &= ~(1u << k);
                 a[k] *= s;
                 b[k] *= s;
             }
@@ -162,6 +171,12 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
             o[0] += q0.x; o[1] += q0.y; o[2] += q0.z; o[3] += q0.w;
             o[4] += q1.x; o[5] += q1.y; o[6] += q1.z; o[7] += q1.w;
         }
+        if (p.save_mask) {
+            uint32_t on = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) on |= ((!p.relu || o[k] > 0.0f) ? 1u : 0u) << k;
+            p.save_mask[(n * p.HW + r) * (long long)p.CB + j] = (uint8_t)(on & kept);
+        }
         if (p.relu) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.0f);
@@ -180,12 +195,174 @@ __global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Backward of gn_act_kernel for the training forward (the autograd half of SURVEY row f4).
+// With z = (x + bias_c - mean_g) * rstd_g, y = on * s * (z * gamma_c + beta_c [+ res]):
+//   dy'      = (g16 + g32) * on * s                  (on: saved ReLU/Dropout2d bit, s = 1/(1-p))
+//   dgamma_c = sum dy' * z,  dbeta_c = sum dy',  dres = dy'
+//   dx       = rstd_g * (dy' * gamma_c - mean_g(dy' gamma) - z * mean_g(dy' gamma z)),  dbias_c = sum dx
+// One CTA per sample; per-channel sums leave the CTA as per-sample partials [n][C] that the host
+// reduces over n in a fixed order (no float atomics -> reproducible).
+// ---------------------------------------------------------------------------
+struct GnBwdParams {
+    const __half *x;            // [n][HW][C] conv output saved by the forward
+    const float *cbias, *gamma; // [C] (cbias nullable)
+    const float *mean, *rstd;   // [n][G]
+    const uint8_t *mask;        // [n][HW][C/8]
+    const __half *g16;          // nullable upstream gradient of y16
+    const float *g32;           // nullable upstream gradient of y32
+    __half *dx;                 // [n][HW][C]
+    float *dres;                // nullable [n][HW][C]
+    float *p_dgamma, *p_dbeta, *p_dbias;   // [n][C] per-sample partials (p_dbias nullable)
+    int HW, C, G, cpg, CB, PPB;
+    float inv_count, scale;
+};
+
+__global__ void __launch_bounds__(256) gn_act_bwd_kernel(const GnBwdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);                              // x, [HW][CB]
+    float *s_g1 = reinterpret_cast<float *>(smem_raw + (size_t)p.HW * p.C * 2);     // [G]
+    float *s_g2 = s_g1 + p.G;
+    float *s_part = s_g2 + p.G;                                                     // [256]
+    float *s_ch = s_part + 256;                                                     // [3][PPB][C]
+
+    const int tid = threadIdx.x;
+    const int j = tid % p.CB, r0 = tid / p.CB;
+    const bool active = r0 < p.PPB;
+    const int g = (j * 8) / p.cpg;
+    const long long n = blockIdx.x;
+    const long long base = n * (long long)p.HW * p.CB;
+    auto group_total = [&](float mine, float *dst) {
+        s_part[tid] = active ? mine : 0.0f;
+        __syncthreads();
+        if (tid < p.G) {
+            const int j0 = tid * (p.cpg / 8), j1 = j0 + p.cpg / 8;
+            float t = 0.0f;
+            for (int r = 0; r < p.PPB; ++r)
+                for (int jj = j0; jj < j1; ++jj) t += s_part[r * p.CB + jj];
+            dst[tid] = t;
+        }
+        __syncthreads();
+    };
+
+    const float mean = p.mean[n * p.G + g], rstd = p.rstd[n * p.G + g];
+    float cb[8], gam[8], dg[8], db[8], dcb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        cb[k] = ((p.cbias && active) ? p.cbias[j * 8 + k] : 0.0f) - mean;
+        gam[k] = active ? p.gamma[j * 8 + k] : 0.0f;
+        dg[k] = db[k] = dcb[k] = 0.0f;
+    }
+    const uint4 *xs = reinterpret_cast<const uint4 *>(p.x) + base;
+    const uint4 *g16 = p.g16 ? reinterpret_cast<const uint4 *>(p.g16) + base : nullptr;
+    const float4 *g32 = p.g32 ? reinterpret_cast<const float4 *>(p.g32) + 2 * base : nullptr;
+    const uint8_t *mk = p.mask + base;
+
+    auto load_dy = [&](int idx, float (&dy)[8]) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dy[k] = 0.0f;
+        if (g16) {
+            const uint4 v = __ldg(g16 + idx);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                dy[2 * k] += f.x; dy[2 * k + 1] += f.y;
+            }
+        }
+        if (g32) {
+            const float4 q0 = __ldg(g32 + 2 * idx), q1 = __ldg(g32 + 2 * idx + 1);
+            dy[0] += q0.x; dy[1] += q0.y; dy[2] += q0.z; dy[3] += q0.w;
+            dy[4] += q1.x; dy[5] += q1.y; dy[6] += q1.z; dy[7] += q1.w;
+        }
+        const uint32_t on = mk[idx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dy[k] = ((on >> k) & 1u) ? dy[k] * p.scale : 0.0f;
+    };
+
+    // pass A: group sums of dy*gamma and dy*gamma*z; per-channel dgamma / dbeta
+    float s1 = 0.0f, s2 = 0.0f;
+    if (active) {
+        for (int r = r0; r < p.HW; r += p.PPB) {
+            const int idx = r * p.CB + j;
+            const uint4 v = __ldcs(xs + idx);
+            tile[idx] = v;
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+            float dy[8];
+            load_dy(idx, dy);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                const float z0 = (f.x + cb[2 * k]) * rstd, z1 = (f.y + cb[2 * k + 1]) * rstd;
+                const float a0 = dy[2 * k] * gam[2 * k], a1 = dy[2 * k + 1] * gam[2 * k + 1];
+                s1 += a0 + a1;
+                s2 += a0 * z0 + a1 * z1;
+                dg[2 * k] += dy[2 * k] * z0; dg[2 * k + 1] += dy[2 * k + 1] * z1;
+                db[2 * k] += dy[2 * k];      db[2 * k + 1] += dy[2 * k + 1];
+            }
+        }
+    }
+    group_total(s1, s_g1);
+    group_total(s2, s_g2);
+    const float m1 = s_g1[g] * p.inv_count, m2 = s_g2[g] * p.inv_count;
+
+    // pass B: dx (and dres), per-channel dbias
+    if (active) {
+        uint4 *dxo = reinterpret_cast<uint4 *>(p.dx) + base;
+        float4 *dro = p.dres ? reinterpret_cast<float4 *>(p.dres) + 2 * base : nullptr;
+        for (int r = r0; r < p.HW; r += p.PPB) {
+            const int idx = r * p.CB + j;
+            const uint4 v = tile[idx];
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+            float dy[8], dx[8];
+            load_dy(idx, dy);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                const float z0 = (f.x + cb[2 * k]) * rstd, z1 = (f.y + cb[2 * k + 1]) * rstd;
+                dx[2 * k] = rstd * (dy[2 * k] * gam[2 * k] - m1 - z0 * m2);
+                dx[2 * k + 1] = rstd * (dy[2 * k + 1] * gam[2 * k + 1] - m1 - z1 * m2);
+                dcb[2 * k] += dx[2 * k]; dcb[2 * k + 1] += dx[2 * k + 1];
+            }
+            uint4 out;
+            __half2 *oh = reinterpret_cast<__half2 *>(&out);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(dx[2 * k], dx[2 * k + 1]);
+            dxo[idx] = out;
+            if (dro) {
+                dro[2 * idx] = make_float4(dy[0], dy[1], dy[2], dy[3]);
+                dro[2 * idx + 1] = make_float4(dy[4], dy[5], dy[6], dy[7]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s_ch[(0 * p.PPB + r0) * p.C + j * 8 + k] = dg[k];
+            s_ch[(1 * p.PPB + r0) * p.C + j * 8 + k] = db[k];
+            s_ch[(2 * p.PPB + r0) * p.C + j * 8 + k] = dcb[k];
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < p.C; c += blockDim.x) {
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        for (int r = 0; r < p.PPB; ++r) {
+            t0 += s_ch[(0 * p.PPB + r) * p.C + c];
+            t1 += s_ch[(1 * p.PPB + r) * p.C + c];
+            t2 += s_ch[(2 * p.PPB + r) * p.C + c];
+        }
+        p.p_dgamma[n * p.C + c] = t0;
+        p.p_dbeta[n * p.C + c] = t1;
+        if (p.p_dbias) p.p_dbias[n * p.C + c] = t2;
+    }
+}
+
 }  // namespace msw
 
 extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *res32, const float *gamma,
                           const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
-                          float drop_p, uint64_t seed, uint64_t call_id, const uint32_t *epoch, void *stream)
+                          float drop_p, uint64_t seed, uint64_t call_id, const uint32_t *epoch, float *save_mean,
+                          float *save_rstd, uint8_t *save_mask, void *stream)
 {
     using namespace msw;
     if (!x16 || !gamma || !beta || (!y16 && !y32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
@@ -213,8 +390,45 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
     p.call_lo = (uint32_t)call_id; p.call_hi = (uint32_t)(call_id >> 32);
     p.epoch = epoch;
+    if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))
+        return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
+    p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;
     if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: n too large");
     gn_act_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+extern "C" int msw_gn_act_bwd(const void *x16, const float *conv_bias, const float *gamma, const float *mean,
+                              const float *rstd, const uint8_t *mask, const void *g16, const float *g32, void *dx16,
+                              float *dres32, float *part_dgamma, float *part_dbeta, float *part_dbias, int64_t n,
+                              int32_t HW, int32_t C, int32_t G, float drop_p, void *stream)
+{
+    using namespace msw;
+    if (!x16 || !gamma || !mean || !rstd || !mask || !dx16 || !part_dgamma || !part_dbeta || (!g16 && !g32))
+        return fail(MSW_ERR_NULL, "msw_gn_act_bwd: NULL pointer");
+    if (n < 0 || HW < 1 || C < 8 || G < 1 || C % G != 0 || C % 8 != 0 || (C / G) % 8 != 0 || C / 8 > 256 || 2 * G > 256)
+        return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act_bwd: need C %% 8 == 0, (C/G) %% 8 == 0 (C=%d G=%d HW=%d)", C, G, HW);
+    if (drop_p < 0.0f || drop_p >= 1.0f) return fail(MSW_ERR_ARG, "msw_gn_act_bwd: drop_p=%f", drop_p);
+    if ((((uintptr_t)x16 | (uintptr_t)g16 | (uintptr_t)g32 | (uintptr_t)dx16 | (uintptr_t)dres32) & 15u) != 0)
+        return fail(MSW_ERR_ALIGN, "msw_gn_act_bwd: tensors must be 16-byte aligned");
+    if (n == 0) return MSW_OK;
+    GnBwdParams p;
+    p.x = (const __half *)x16; p.cbias = conv_bias; p.gamma = gamma; p.mean = mean; p.rstd = rstd; p.mask = mask;
+    p.g16 = (const __half *)g16; p.g32 = g32; p.dx = (__half *)dx16; p.dres = dres32;
+    p.p_dgamma = part_dgamma; p.p_dbeta = part_dbeta; p.p_dbias = part_dbias;
+    p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.CB = C / 8; p.PPB = 256 / p.CB;
+    p.inv_count = 1.0f / (float)((long long)HW * p.cpg);
+    p.scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 256 + 3 * (size_t)p.PPB * C) * sizeof(float);
+    if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act_bwd: sample of %zu bytes does not fit shared memory", smem);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        MSW_CUDA_TRY(cudaFuncSetAttribute(gn_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act_bwd: n too large");
+    gn_act_bwd_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

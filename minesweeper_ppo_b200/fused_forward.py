@@ -42,7 +42,8 @@ def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[t
                           norm.bias.data_ptr(), None if y16 is None else y16.data_ptr(),
                           None if y32 is None else y32.data_ptr(), N, H * W, C, norm.num_groups, float(norm.eps),
                           int(relu), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFFFFFFFFFF,
-                          None if epoch is None else epoch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                          None if epoch is None else epoch.data_ptr(), None, None, None,
+                          torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "msw_gn_act")
     return y16, y32
 

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import fused_train as fused_train_mod
 from .buffers import RolloutBuffer
 from .env import EnvConfig, VecMinesweeper
 from .policy import build_model
@@ -90,16 +91,17 @@ def load_config(path: Optional[str]):
     return cfg, env_d, model_d, extras
 
 
-def ppo_loss(model, batch, cfg: PPOConfig):
+def ppo_loss(model, batch, cfg: PPOConfig, forward=None):
     """Clipped-ratio policy loss + clipped value loss - entropy bonus + auxiliary mine-belief
     BCE / Brier terms, as ppo.py:23-95 (fp16 autocast on CUDA, no advantage normalisation)."""
     on_cuda = batch.obs.is_cuda
     with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=on_cuda):
         want_mine = cfg.aux_mine_weight > 0 or cfg.aux_mine_calib_weight > 0
+        fwd = forward if forward is not None else model      # `forward`: e.g. the fused training forward
         if want_mine:
-            logits, value, mine_logits = model(batch.obs, return_mine=True)
+            logits, value, mine_logits = fwd(batch.obs, return_mine=True)
         else:
-            (logits, value), mine_logits = model(batch.obs, return_mine=False), None
+            (logits, value), mine_logits = fwd(batch.obs, return_mine=False), None
         fill = -1e4 if logits.dtype in (torch.float16, torch.bfloat16) else -1e9
         masked = logits.masked_fill(~batch.action_mask, fill)
         logp_all = F.log_softmax(masked, dim=-1)
@@ -160,10 +162,10 @@ class FlatGradAllReduce:
 
 
 def ppo_update(model, optimizer, batch, cfg: PPOConfig, scaler=None, grads: Optional[FlatGradAllReduce] = None,
-               want_stats: bool = True) -> Dict[str, float]:
+               want_stats: bool = True, forward=None) -> Dict[str, float]:
     """One optimizer step (ppo.py:96-119) with the gradient all-reduce between backward and
     unscale/clip."""
-    loss, stats = ppo_loss(model, batch, cfg)
+    loss, stats = ppo_loss(model, batch, cfg, forward=forward)
     optimizer.zero_grad(set_to_none=True)
     if scaler is not None and batch.obs.is_cuda:
         scaler.scale(loss).backward()
@@ -183,7 +185,7 @@ def ppo_update(model, optimizer, batch, cfg: PPOConfig, scaler=None, grads: Opti
 
 
 def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], steps: Optional[int], seed: int = 0,
-          log: Callable[[str], None] = print) -> Dict[str, float]:
+          log: Callable[[str], None] = print, fused_train: bool = True) -> Dict[str, float]:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,6 +217,12 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
     collector = RolloutCollector(vec, T, aux_maps=need_aux, sample_seed=seed, graph=RolloutCollector.can_graph(model))
     grads = FlatGradAllReduce(model)
     mb = (n_local * T) // cfg.mini_batches
+    opt_step = [0]
+    train_fwd = None
+    if fused_train and fused_train_mod.supports(model):      # fused GroupNorm forward + backward
+        def train_fwd(obs, return_mine=False):
+            opt_step[0] += 1
+            return fused_train_mod.fused_train_forward(model, obs, return_mine, seed=seed + 7919 * rank, step=opt_step[0])
 
     def sync():
         if world > 1:
@@ -234,7 +242,7 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
         sync(); t1 = time.perf_counter()
         for _ in range(cfg.ppo_epochs):
             for batch in buf.get_minibatches(mb):
-                last = ppo_update(model, opt, batch, pcfg, scaler, grads, want_stats=False)
+                last = ppo_update(model, opt, batch, pcfg, scaler, grads, want_stats=False, forward=train_fwd)
         sched.step()
         sync(); t2 = time.perf_counter()
         if u >= timed_from:
@@ -259,6 +267,7 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
         "ms_rollout_gae": 1e3 * t_roll / n_timed, "ms_ppo_epochs": 1e3 * t_upd / n_timed,
         "optimizer_steps_per_update": cfg.ppo_epochs * cfg.mini_batches,
         "grad_allreduce_bytes": grads.numel * 4, "replica_param_checksum_spread": spread,
+        "training_forward": "fused GroupNorm fwd+bwd (msw_gn_act / msw_gn_act_bwd)" if train_fwd else "eager module",
     }
     if world > 1:
         dist.destroy_process_group()
@@ -272,8 +281,10 @@ def main() -> None:
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--eager-train", action="store_true", help="use the unchanged module for the PPO update")
     a = ap.parse_args()
-    r = train(a.config, a.updates, a.envs_per_gpu, a.steps, a.seed, log=lambda s: print(s, flush=True))
+    r = train(a.config, a.updates, a.envs_per_gpu, a.steps, a.seed, log=lambda s: print(s, flush=True),
+              fused_train=not a.eager_train)
     if r:
         print(json.dumps(r), flush=True)
 

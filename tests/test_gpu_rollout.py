@@ -263,3 +263,72 @@ def test_graph_captured_rollout(oracle):
         P.assert_bits_equal(c(b2.dones[s]), d, f"slot {t} dones")
         obs, mask, lab = bb["obs"], bb["action_mask"], ref.mine_labels
     assert aux["last_values"].shape == (N,)
+
+
+def test_gn_act_autograd_matches_torch():
+    """msw_gn_act + msw_gn_act_bwd as an autograd Function vs torch autograd of the same expression in
+    fp32 (relu(group_norm(x + bias) + res)), with upstream gradients on both outputs."""
+    import torch
+    import torch.nn.functional as F
+    from minesweeper_ppo_b200.fused_train import GnAct
+    torch.manual_seed(0)
+    for (N, C, G, H, W, with_res) in [(8, 96, 6, 16, 16, True), (5, 32, 2, 5, 7, False), (3, 128, 8, 8, 8, True)]:
+        x = torch.randn(N, C, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last).requires_grad_()
+        cb = torch.randn(C, device="cuda", requires_grad=True)
+        gam = (torch.rand(C, device="cuda") + 0.5).requires_grad_()
+        bet = torch.randn(C, device="cuda", requires_grad=True)
+        res = torch.randn(N, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_() if with_res else None
+        y16, y32 = GnAct.apply(x, cb, gam, bet, res, G, 1e-5, True, 0.0, 0, 0, True)
+        u16 = torch.randn_like(y16); u32 = torch.randn_like(y32)
+        ((y16.float() * u16.float()).sum() + (y32 * u32).sum()).backward()
+        got = [t.grad.clone() for t in (x, cb, gam, bet)] + ([res.grad.clone()] if with_res else [])
+        for t in (x, cb, gam, bet) + ((res,) if with_res else ()):
+            t.grad = None
+        z = F.group_norm(x.float() + cb.view(1, C, 1, 1), G, gam, bet, 1e-5)
+        ref = torch.relu(z + res) if with_res else torch.relu(z)
+        assert float((y32 - ref).abs().max()) <= 2e-5 * (float(ref.abs().max()) + 1)
+        # the kernel sees one upstream gradient per element: g16 (fp16) + g32
+        (ref * (u16.float() + u32)).sum().backward()
+        want = [t.grad for t in (x, cb, gam, bet)] + ([res.grad] if with_res else [])
+        names = ["dx", "dbias", "dgamma", "dbeta", "dres"]
+        for a, b, nm in zip(got, want, names):
+            err = float((a.float() - b.float()).abs().max())
+            scale = float(b.float().abs().max()) + 1e-6
+            tol = 4e-3 if nm == "dx" else 2e-4            # dx is rounded to fp16
+            assert err <= tol * scale, (nm, err, scale, (N, C, G, H, W))
+
+
+def test_fused_train_forward_gradients_match_autocast_module():
+    """Whole-network check: loss gradients w.r.t. every parameter through the fused training forward
+    vs the unchanged module under fp16 autocast (the reference's ppo_update path, ppo.py:24-26)."""
+    import torch
+    import minesweeper_ppo_b200 as m
+    from minesweeper_ppo_b200.fused_train import fused_train_forward
+    torch.manual_seed(3)
+    net = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
+                        model_cfg=dict(stem_channels=96, blocks=3, dropout=0.0, value_hidden=64)).cuda()
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.GroupNorm):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.uniform_(-0.3, 0.3)
+    x = (torch.rand(48, 10, 16, 16, device="cuda") < 0.3).float()
+    wl, wv, wm = torch.randn(48, 256, device="cuda"), torch.randn(48, device="cuda"), torch.randn(48, 1, 16, 16, device="cuda")
+
+    def loss_of(outs):
+        l, v, mi = outs
+        return (l.float() * wl).mean() + (v.float() * wv).mean() + (mi.float() * wm).mean()
+
+    with torch.autocast("cuda", dtype=torch.float16):
+        ref_out = net(x, return_mine=True)
+    loss_of(ref_out).backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    out = fused_train_forward(net, x, return_mine=True)
+    for a, b in zip(out, ref_out):
+        assert float((a.float() - b.float()).abs().max()) <= 2e-2 * (float(b.float().abs().max()) + 1e-3)
+    loss_of(out).backward()
+    for k, p in net.named_parameters():
+        g, r = p.grad.float().reshape(-1), ref[k].float().reshape(-1)
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+        rel = float((g - r).norm() / (r.norm() + 1e-30))
+        assert cos > 0.995 and rel < 0.1, (k, cos, rel)      # both paths carry fp16 rounding noise
