@@ -81,26 +81,36 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # pragma: no cover
             self.nv, self.err = None, repr(e)
 
+    def sample_once(self):
+        nv = self.nv
+        self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for bit, name in self.REASONS.items():
+            if r & bit:
+                self.reasons.add(name)
+
     def run(self):
         if self.nv is None:
             return
-        nv = self.nv
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.sample_once()
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
             self._stop_evt.wait(self.period)
 
     def finish(self):
+        """Call while the GPU is still busy with the timed region (before the final synchronize), so
+        even a very short region gets at least one sample under load."""
+        if self.nv is not None and self.err is None:
+            try:
+                self.sample_once()
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
         self._stop_evt.set()
         self.join(timeout=2)
         out = {"sm_mhz": (float(np.median(self.samples)) if self.samples else None), "sm_max_mhz": self.sm_max,
@@ -230,8 +240,8 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         vec.step_random(Wm + t, valid_only=VALID_ONLY, out=slots[t % ring], actions_out=a)   # policy + step: one launch
         kev[t][1].record()
     ev1.record()
+    clocks = sampler.finish()          # sampled while the last launches are still executing
     barrier()
-    clocks = sampler.finish()
     ms_total = ev0.elapsed_time(ev1)
     ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / K
     episodes = None
