@@ -27,6 +27,19 @@
 
 namespace msw {
 
+// 16-byte asynchronous global->shared copy (LDGSTS): staging a whole [HW][C] sample this way puts
+// every thread's ~12 loads in flight at once instead of one at a time (ncu: the synchronous loop
+// left the kernel at half the HBM rate).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 struct GnParams {
     const __half *x;        // [n][HW][C]
     const float *cbias;     // nullable [C]: bias of the convolution that produced x, added before the norm
@@ -44,153 +57,164 @@ struct GnParams {
     uint8_t *save_mask;             // [n][HW][C/8]: bit k of a byte = output channel 8j+k is "on" (ReLU active, not dropped)
 };
 
-__global__ void __launch_bounds__(256) gn_act_kernel(const GnParams p)
+__global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long long n_samples)
 {
+    // One CTA per sample, 4 CTAs per SM (48 registers, ~50 KB of shared memory each).  A persistent,
+    // double-buffered variant (2 tiles per CTA, next sample prefetched during the current one's
+    // compute + store) was measured SLOWER (5.0 vs 4.0 ms per forward): it halves the resident warps,
+    // and the latency-bound statistics / normalise phases need them more than the loads need overlap.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *tile = reinterpret_cast<uint4 *>(smem_raw);                       // [HW][CB] chunks of 8 halves
-    float *s_sum = reinterpret_cast<float *>(smem_raw + (size_t)p.HW * p.C * 2);   // [G]
+    const size_t tile_bytes = (size_t)p.HW * p.C * 2;
+    float *s_sum = reinterpret_cast<float *>(smem_raw + tile_bytes);              // [G]
     float *s_sq = s_sum + p.G;
-    float *s_part = s_sq + p.G;                                                   // [256] per-thread partials
+    float *s_part = s_sq + p.G;                                                   // [3][256] per-thread partials
 
     const int tid = threadIdx.x;
     const int j = tid % p.CB, r0 = tid / p.CB;
     const bool active = r0 < p.PPB;
     const int g = (j * 8) / p.cpg;
+    float cb0[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cb0[k] = (p.cbias && active) ? p.cbias[j * 8 + k] : 0.0f;
+    auto stage = [&](long long s, int buf) {            // each thread copies (and later reads) only its own chunks
+        if (active) {
+            uint4 *tile = reinterpret_cast<uint4 *>(smem_raw + buf * tile_bytes);
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.x) + s * (long long)p.HW * p.CB;
+            for (int r = r0; r < p.HW; r += p.PPB) cp_async16(tile + r * p.CB + j, src + r * p.CB + j);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
     const long long n = blockIdx.x;
-    const long long base = n * (long long)p.HW * p.CB;                       // in uint4 chunks
-    // Group totals are formed from the per-thread partials in a FIXED order (no float atomics), so
-    // the kernel is bitwise reproducible run to run, like the eager GroupNorm it replaces.
-    auto group_total = [&](float mine, float *dst) {
-        s_part[tid] = active ? mine : 0.0f;
+    const int buf = 0;
+    if (n < n_samples) {
+        stage(n, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint4 *tile = reinterpret_cast<const uint4 *>(smem_raw + buf * tile_bytes);
+        const long long base = n * (long long)p.HW * p.CB;                       // in uint4 chunks
+
+        // ONE pass for the statistics: per thread, shifted sums S1 = sum (v - c), S2 = sum (v - c)^2 of
+        // v = x + conv_bias with c = the thread's first value (no cancellation in S2 - S1^2/m); the
+        // per-thread (count, mean, M2) triples of a group are merged with Chan's update in a FIXED order
+        // by one thread per group -- no float atomics, bitwise reproducible like the eager GroupNorm.
+        float cnt = 0.0f, tmean = 0.0f, tm2 = 0.0f;
+        if (active) {
+            float c0 = 0.0f, S1 = 0.0f, S2 = 0.0f;
+            bool have_shift = false;
+            for (int r = r0; r < p.HW; r += p.PPB) {
+                const uint4 v = tile[r * p.CB + j];
+                const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+                if (!have_shift) {
+                    c0 = __low2float(h[0]) + cb0[0];
+                    have_shift = true;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h[k]);
+                    const float d0 = (f.x + cb0[2 * k]) - c0, d1 = (f.y + cb0[2 * k + 1]) - c0;
+                    S1 += d0 + d1;
+                    S2 = fmaf(d0, d0, fmaf(d1, d1, S2));
+                }
+                cnt += 8.0f;
+            }
+            if (cnt > 0.0f) {
+                tmean = c0 + S1 / cnt;
+                tm2 = S2 - S1 * S1 / cnt;
+            }
+        }
+        s_part[tid] = cnt;
+        s_part[256 + tid] = tmean;
+        s_part[512 + tid] = tm2;
         __syncthreads();
         if (tid < p.G) {
             const int j0 = tid * (p.cpg / 8), j1 = j0 + p.cpg / 8;
-            float t = 0.0f;
+            float na = 0.0f, ma = 0.0f, qa = 0.0f;
             for (int r = 0; r < p.PPB; ++r)
-                for (int jj = j0; jj < j1; ++jj) t += s_part[r * p.CB + jj];
-            dst[tid] = t;
+                for (int jj = j0; jj < j1; ++jj) {
+                    const int t = r * p.CB + jj;
+                    const float nb = s_part[t];
+                    if (nb > 0.0f) {
+                        const float nn = na + nb, delta = s_part[256 + t] - ma;
+                        ma += delta * (nb / nn);
+                        qa += s_part[512 + t] + delta * delta * (na * nb / nn);
+                        na = nn;
+                    }
+                }
+            s_sum[tid] = ma;                                        // group mean of (x + conv_bias)
+            s_sq[tid] = rsqrtf(qa * p.inv_count + p.eps);           // group rstd (biased variance, eps as torch)
+            if (p.save_mean) {
+                p.save_mean[n * p.G + tid] = ma;
+                p.save_rstd[n * p.G + tid] = s_sq[tid];
+            }
         }
         __syncthreads();
-    };
-
-    // pass 0: stage the sample, accumulate sums.  The conv bias (a per-channel constant) is folded
-    // in analytically: it shifts the group mean by the mean of the group's biases and each channel
-    // by (bias_c - that mean); the staged tile keeps the raw conv output.
-    float cb[8];
+        if (active) {
+            const float mean = s_sum[g], rstd = s_sq[g];
+            // per-channel affine folded with the statistics, and the Dropout2d channel mask
+            float a[8], b[8];
+            uint32_t kept = 0xFFu;                                    // channels that survive Dropout2d
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (p.drop_p > 0.0f)
+                philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo,
+                              p.call_hi + (p.epoch ? *p.epoch : 0u), w);
+            const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cb[k] = (p.cbias && active) ? p.cbias[j * 8 + k] : 0.0f;
-    float acc = 0.0f;
-    if (active) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.x) + base;
-        int rows = 0;
-        for (int r = r0; r < p.HW; r += p.PPB) {
-            const uint4 v = __ldcs(src + r * p.CB + j);
-            tile[r * p.CB + j] = v;
-            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
-                acc += f.x + f.y;
+            for (int k = 0; k < 8; ++k) {
+                const float ga = p.gamma[j * 8 + k] * rstd;
+                a[k] = ga;
+                b[k] = fmaf(cb0[k] - mean, ga, p.beta[j * 8 + k]);  // beta + (bias_c - mean) * gamma * rstd
+                if (p.drop_p > 0.0f) {
+                    // relu(z)*s == relu(z*s) for s >= 0, so the mask/scale folds into the affine when no
+                    // residual is added (Dropout2d follows ReLU only on that path, cnn_residual.py:20-21)
+                    const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    const float sc = (u16 < thresh) ? 0.0f : p.drop_scale;
+                    if (u16 < thresh) kept &= ~(1u << k);
+                    a[k] *= sc;
+                    b[k] *= sc;
+                }
             }
-            ++rows;
-        }
-        float bsum = 0.0f;
+            const float4 *__restrict__ res = p.res ? reinterpret_cast<const float4 *>(p.res) + 2 * base : nullptr;
+            uint4 *__restrict__ y16 = p.y16 ? reinterpret_cast<uint4 *>(p.y16) + base : nullptr;
+            float4 *__restrict__ y32 = p.y32 ? reinterpret_cast<float4 *>(p.y32) + 2 * base : nullptr;
+#pragma unroll 4
+            for (int r = r0; r < p.HW; r += p.PPB) {
+                const int idx = r * p.CB + j;
+                const uint4 v = tile[idx];
+                const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+                float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bsum += cb[k];
-        acc += bsum * (float)rows;
-    }
-    group_total(acc, s_sum);
-    const float mean = s_sum[g] * p.inv_count;
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h[k]);
+                    o[2 * k] = fmaf(f.x, a[2 * k], b[2 * k]);
+                    o[2 * k + 1] = fmaf(f.y, a[2 * k + 1], b[2 * k + 1]);
+                }
+                if (res) {
+                    const float4 q0 = __ldcs(res + 2 * idx), q1 = __ldcs(res + 2 * idx + 1);
+                    o[0] += q0.x; o[1] += q0.y; o[2] += q0.z; o[3] += q0.w;
+                    o[4] += q1.x; o[5] += q1.y; o[6] += q1.z; o[7] += q1.w;
+                }
+                if (p.save_mask) {
+                    uint32_t on = 0u;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cb[k] -= mean;                 // (x + bias_c) - mean == x + cb[k]
-
-    // pass 1: centred second moment (two-pass variance, like torch's RowwiseMoments)
-    acc = 0.0f;
-    if (active) {
-        for (int r = r0; r < p.HW; r += p.PPB) {
-            const uint4 v = tile[r * p.CB + j];
-            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+                    for (int k = 0; k < 8; ++k) on |= ((!p.relu || o[k] > 0.0f) ? 1u : 0u) << k;
+                    p.save_mask[(n * p.HW + r) * (long long)p.CB + j] = (uint8_t)(on & kept);
+                }
+                if (p.relu) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
-                const float a = f.x + cb[2 * k], b = f.y + cb[2 * k + 1];
-                acc += a * a + b * b;
+                    for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.0f);
+                }
+                if (y32) {
+                    y32[2 * idx] = make_float4(o[0], o[1], o[2], o[3]);
+                    y32[2 * idx + 1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (y16) {
+                    uint4 out;
+                    __half2 *oh = reinterpret_cast<__half2 *>(&out);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+                    y16[idx] = out;
+                }
             }
-        }
-    }
-    group_total(acc, s_sq);
-    if (p.save_mean && tid < p.G) {
-        p.save_mean[n * p.G + tid] = s_sum[tid] * p.inv_count;
-        p.save_rstd[n * p.G + tid] = rsqrtf(s_sq[tid] * p.inv_count + p.eps);
-    }
-    if (!active) return;
-    const float rstd = rsqrtf(s_sq[g] * p.inv_count + p.eps);
-
-    // per-channel affine folded with the statistics, and the Dropout2d channel mask
-    float a[8], b[8];
-    uint32_t kept = 0xFFu;                                    // channels that survive Dropout2d
-    {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (p.drop_p > 0.0f)
-            philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo,
-                          p.call_hi + (p.epoch ? *p.epoch : 0u), w);
-        const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = j * 8 + k;
-            const float ga = p.gamma[c] * rstd;
-            a[k] = ga;
-            b[k] = fmaf(cb[k], ga, p.beta[c]);                  // beta + (bias_c - mean) * gamma * rstd
-            const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if (p.drop_p > 0.0f) {
-                // relu(z)*s == relu(z*s) for s >= 0, so the mask/scale folds into the affine when no
-                // residual is added (Dropout2d follows ReLU only on that path, cnn_residual.py:20-21)
-                const float s = (u16 < thresh) ? 0.0f : p.drop_scale;
-                if (u16 < thresh) kept &= ~(1u << k);
-                a[k] *= s;
-                b[k] *= s;
-            }
-        }
-    }
-    const float4 *res = p.res ? reinterpret_cast<const float4 *>(p.res) + 2 * base : nullptr;
-    uint4 *y16 = p.y16 ? reinterpret_cast<uint4 *>(p.y16) + base : nullptr;
-    float4 *y32 = p.y32 ? reinterpret_cast<float4 *>(p.y32) + 2 * base : nullptr;
-    for (int r = r0; r < p.HW; r += p.PPB) {
-        const int idx = r * p.CB + j;
-        const uint4 v = tile[idx];
-        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
-        float o[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(h[k]);
-            o[2 * k] = fmaf(f.x, a[2 * k], b[2 * k]);
-            o[2 * k + 1] = fmaf(f.y, a[2 * k + 1], b[2 * k + 1]);
-        }
-        if (res) {
-            const float4 q0 = __ldcs(res + 2 * idx), q1 = __ldcs(res + 2 * idx + 1);
-            o[0] += q0.x; o[1] += q0.y; o[2] += q0.z; o[3] += q0.w;
-            o[4] += q1.x; o[5] += q1.y; o[6] += q1.z; o[7] += q1.w;
-        }
-        if (p.save_mask) {
-            uint32_t on = 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) on |= ((!p.relu || o[k] > 0.0f) ? 1u : 0u) << k;
-            p.save_mask[(n * p.HW + r) * (long long)p.CB + j] = (uint8_t)(on & kept);
-        }
-        if (p.relu) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.0f);
-        }
-        if (y32) {
-            y32[2 * idx] = make_float4(o[0], o[1], o[2], o[3]);
-            y32[2 * idx + 1] = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        if (y16) {
-            uint4 out;
-            __half2 *oh = reinterpret_cast<__half2 *>(&out);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
-            y16[idx] = out;
         }
     }
 }
@@ -284,10 +308,12 @@ __global__ void __launch_bounds__(256) gn_act_bwd_kernel(const GnBwdParams p)
     // pass A: group sums of dy*gamma and dy*gamma*z; per-channel dgamma / dbeta
     float s1 = 0.0f, s2 = 0.0f;
     if (active) {
+        for (int r = r0; r < p.HW; r += p.PPB) cp_async16(tile + r * p.CB + j, xs + r * p.CB + j);
+        cp_async_wait_all();
+#pragma unroll 2
         for (int r = r0; r < p.HW; r += p.PPB) {
             const int idx = r * p.CB + j;
-            const uint4 v = __ldcs(xs + idx);
-            tile[idx] = v;
+            const uint4 v = tile[idx];
             const __half2 *h = reinterpret_cast<const __half2 *>(&v);
             float dy[8];
             load_dy(idx, dy);
@@ -311,6 +337,7 @@ __global__ void __launch_bounds__(256) gn_act_bwd_kernel(const GnBwdParams p)
     if (active) {
         uint4 *dxo = reinterpret_cast<uint4 *>(p.dx) + base;
         float4 *dro = p.dres ? reinterpret_cast<float4 *>(p.dres) + 2 * base : nullptr;
+#pragma unroll 2
         for (int r = r0; r < p.HW; r += p.PPB) {
             const int idx = r * p.CB + j;
             const uint4 v = tile[idx];
@@ -373,7 +400,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     if ((((uintptr_t)x16 | (uintptr_t)res32 | (uintptr_t)y16 | (uintptr_t)y32) & 15u) != 0)
         return fail(MSW_ERR_ALIGN, "msw_gn_act: tensors must be 16-byte aligned");
     if (n == 0) return MSW_OK;
-    const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 256) * sizeof(float);
+    const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 3 * 256) * sizeof(float);
     if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: sample of %zu bytes does not fit shared memory", smem);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -394,7 +421,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
         return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;
     if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: n too large");
-    gn_act_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
+    gn_act_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p, (long long)n);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }
