@@ -10,56 +10,61 @@
 //     last  = delta + ((gamma*lam) * nnt) * last                      (:91)
 //     returns = advantages + values                                   (:94)
 // Storage is time-major [T][N] (buffers.py:81-83), so a row of 32 consecutive
-// columns is one 128-byte line.  A CTA owns 32 columns: all 8 warps stream the
-// [TC x 32] tiles of rewards / values / dones into shared memory with coalesced
-// loads (the only way to get enough bytes in flight when N is a few thousand
-// columns), warp 0 walks the chain out of shared memory, and all warps write
-// advantages / returns back coalesced.  HBM-bound in principle (17 B per
+// columns is one 128-byte line.  A CTA owns 16 or 32 columns: all 8 warps stream
+// the [TC x COLS] tiles of rewards / values / dones into shared memory with
+// coalesced loads (the only way to get enough bytes in flight when N is a few
+// thousand columns), one warp walks the chains out of shared memory, and all
+// warps write advantages / returns back coalesced.  HBM-bound in principle (17 B per
 // transition) but latency-bound at the reference's sizes.
 #include "../../include/msw_b200.h"
 #include "msw_error.h"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace msw {
 
-constexpr int GAE_COLS = 32;    // columns per CTA (one 128 B line per row)
 constexpr int GAE_TC = 128;     // time rows per shared-memory chunk
-constexpr int GAE_WARPS = 8;
+constexpr int GAE_THREADS = 256;
 
-__global__ void __launch_bounds__(GAE_WARPS * 32)
+// COLS env columns per CTA (16 or 32).  Thread t loads column t % COLS of rows t / COLS,
+// t / COLS + 256 / COLS, ...; the first COLS lanes of warp 0 walk the chains.
+template <int COLS>
+__global__ void __launch_bounds__(GAE_THREADS)
 gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
            const uint8_t *__restrict__ dones, const float *__restrict__ last_values,
            float *__restrict__ adv, float *__restrict__ ret, long long T, long long N,
            float gamma, float gamma_lam, int prescaled)
 {
-    __shared__ float s_r[GAE_TC][GAE_COLS];     // rewards in, advantages out
-    __shared__ float s_v[GAE_TC][GAE_COLS];
-    __shared__ uint8_t s_d[GAE_TC][GAE_COLS];
+    __shared__ float s_r[GAE_TC][COLS];     // rewards in, advantages out
+    __shared__ float s_v[GAE_TC][COLS];
+    __shared__ uint8_t s_d[GAE_TC][COLS];
+    constexpr int RPP = GAE_THREADS / COLS;       // rows per pass of the whole CTA
+    constexpr int RPT = GAE_TC / RPP;             // rows per thread and chunk
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long col = (long long)blockIdx.x * GAE_COLS + lane;
+    const int c = threadIdx.x % COLS;
+    const int rr = threadIdx.x / COLS;
+    const long long col = (long long)blockIdx.x * COLS + c;
     const bool in = col < N;
-    constexpr int RPW = GAE_TC / GAE_WARPS;     // rows per warp and chunk (16)
+    const bool chain = threadIdx.x < COLS;        // warp 0, first COLS lanes
 
     float last = 0.0f;                                          // buffers.py:86
-    float next_value = in ? last_values[col] : 0.0f;            // buffers.py:88 (t == T-1)
+    float next_value = (chain && in) ? last_values[col] : 0.0f; // buffers.py:88 (t == T-1)
     bool scaled = prescaled != 0;       // last_values already is gamma*last_value (fp16 bootstrap)
 
     for (long long t_hi = T; t_hi > 0; t_hi -= GAE_TC) {
         const long long t_lo = t_hi > GAE_TC ? t_hi - GAE_TC : 0;
         const int rows = (int)(t_hi - t_lo);
         __syncthreads();
-        // ---- load: every thread issues all of its (up to 3*RPW) loads before the first use, so a
-        // CTA has its whole 36 KB tile in flight at once (the kernel is latency-, not bandwidth-bound)
+        // ---- load: every thread issues all of its (up to 3*RPT) loads before the first use, so a
+        // CTA has its whole tile in flight at once (the kernel is latency-, not bandwidth-bound)
         {
-            float r[RPW], v[RPW];
-            uint8_t d[RPW];
+            float r[RPT], v[RPT];
+            uint8_t d[RPT];
 #pragma unroll
-            for (int k = 0; k < RPW; ++k) {
-                const int i = warp + k * GAE_WARPS;
+            for (int k = 0; k < RPT; ++k) {
+                const int i = rr + k * RPP;
                 const bool ok = in && i < rows;
                 const long long idx = (t_lo + i) * N + col;
                 r[k] = ok ? __ldcs(rewards + idx) : 0.0f;
@@ -67,25 +72,25 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
                 d[k] = ok ? __ldcs(dones + idx) : (uint8_t)0;
             }
 #pragma unroll
-            for (int k = 0; k < RPW; ++k) {
-                const int i = warp + k * GAE_WARPS;
-                s_r[i][lane] = r[k];
-                s_v[i][lane] = v[k];
-                s_d[i][lane] = d[k];
+            for (int k = 0; k < RPT; ++k) {
+                const int i = rr + k * RPP;
+                s_r[i][c] = r[k];
+                s_v[i][c] = v[k];
+                s_d[i][c] = d[k];
             }
         }
         __syncthreads();
-        // ---- chain: warp 0, 8 rows per batch read into registers ahead of the dependent arithmetic
-        if (warp == 0) {
+        // ---- chain: 8 rows per batch read into registers ahead of the dependent arithmetic
+        if (chain) {
             for (int hi = rows; hi > 0; hi -= 8) {
                 float r[8], v[8], nn[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int i = hi - 1 - k;
                     const bool ok = i >= 0;
-                    r[k] = ok ? s_r[ok ? i : 0][lane] : 0.0f;
-                    v[k] = ok ? s_v[ok ? i : 0][lane] : 0.0f;
-                    nn[k] = (ok && s_d[ok ? i : 0][lane]) ? 0.0f : 1.0f;
+                    r[k] = ok ? s_r[ok ? i : 0][c] : 0.0f;
+                    v[k] = ok ? s_v[ok ? i : 0][c] : 0.0f;
+                    nn[k] = (ok && s_d[ok ? i : 0][c]) ? 0.0f : 1.0f;
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -95,7 +100,7 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
                         scaled = false;
                         const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(gv, nn[k])), v[k]);
                         last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nn[k]), last));
-                        s_r[i][lane] = last;
+                        s_r[i][c] = last;
                         next_value = v[k];
                     }
                 }
@@ -104,13 +109,13 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
         __syncthreads();
         if (in) {
 #pragma unroll
-            for (int k = 0; k < RPW; ++k) {
-                const int i = warp + k * GAE_WARPS;
+            for (int k = 0; k < RPT; ++k) {
+                const int i = rr + k * RPP;
                 if (i < rows) {
                     const long long idx = (t_lo + i) * N + col;
-                    const float a = s_r[i][lane];
+                    const float a = s_r[i][c];
                     __stcs(adv + idx, a);
-                    __stcs(ret + idx, __fadd_rn(a, s_v[i][lane]));
+                    __stcs(ret + idx, __fadd_rn(a, s_v[i][c]));
                 }
             }
         }
@@ -129,11 +134,25 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
         return fail(MSW_ERR_NULL, "msw_gae: NULL pointer");
     if (T < 0 || N < 0) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: T=%lld N=%lld", (long long)T, (long long)N);
     if (T == 0 || N == 0) return MSW_OK;
-    const long long blocks = (N + GAE_COLS - 1) / GAE_COLS;
+    // 32 columns per CTA (one full 128-byte line per row).  16 columns -- twice the CTAs, so every SM
+    // has work at N = 8,192 -- was measured slower (18.4 vs 14.3 us, half-line requests); it stays
+    // selectable through MSW_GAE_COLS=16 for experiments.
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("MSW_GAE_COLS");
+        forced = e ? atoi(e) : 0;
+    }
+    const int cols = forced == 16 ? 16 : 32;
+    const long long blocks = (N + cols - 1) / cols;
     if (blocks > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: N too large");
-    gae_kernel<<<(unsigned)blocks, GAE_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32,
-        (int)last_values_prescaled);
+    if (cols == 16)
+        gae_kernel<16><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(
+            rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32,
+            (int)last_values_prescaled);
+    else
+        gae_kernel<32><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(
+            rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32,
+            (int)last_values_prescaled);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }
