@@ -704,16 +704,15 @@ __global__ void __launch_bounds__(256) random_actions_kernel(const ActParams p)
 // ---------------------------------------------------------------------------
 // Host side of the C ABI
 // ---------------------------------------------------------------------------
-static int fill_params(EnvParams &p, const msw_env_desc *d, const msw_state *st, long long n)
+// Board geometry and env constants (no state pointers).
+static int fill_geometry(EnvParams &p, const msw_env_desc *d, long long n)
 {
-    if (!d || !st) return fail(MSW_ERR_NULL, "desc/state is NULL");
+    if (!d) return fail(MSW_ERR_NULL, "desc is NULL");
     if (d->H < 1 || d->W < 1 || d->W > 32 || (long long)d->H * d->W > MSW_MAX_CELLS)
         return fail(MSW_ERR_BAD_SHAPE, "board %dx%d unsupported (need 1<=W<=32, H*W<=%d)", d->H, d->W, MSW_MAX_CELLS);
     if (d->mine_count < 0 || d->mine_count > d->H * d->W - 1)
         return fail(MSW_ERR_BAD_SHAPE, "mine_count %d out of range for %dx%d", d->mine_count, d->H, d->W);
     if (n < 0) return fail(MSW_ERR_BAD_SHAPE, "n=%lld < 0", n);
-    if (!st->mines || !st->revealed || !st->meta) return fail(MSW_ERR_NULL, "state pointer is NULL");
-    if (((uintptr_t)st->meta & 15u) != 0) return fail(MSW_ERR_ALIGN, "state.meta must be 16-byte aligned");
     memset(&p, 0, sizeof(p));
     p.H = d->H; p.W = d->W; p.HW = d->H * d->W; p.wpb = (p.HW + 31) / 32;
     p.mine_count = d->mine_count; p.safe = d->safe_nbhd != 0;
@@ -722,8 +721,6 @@ static int fill_params(EnvParams &p, const msw_env_desc *d, const msw_state *st,
     p.thresh16 = 65536u % (uint32_t)p.HW;
     p.env_id_base = d->env_id_base;
     p.n = n;
-    p.mines = st->mines; p.revealed = st->revealed; p.flags = st->flags;
-    p.meta = reinterpret_cast<int4 *>(st->meta);
     for (int w = 0; w < 32; ++w) {
         uint32_t v = 0, a = 0, z = 0;
         for (int j = 0; j < 32; ++j) {
@@ -736,6 +733,19 @@ static int fill_params(EnvParams &p, const msw_env_desc *d, const msw_state *st,
         }
         p.g_valid[w] = v; p.g_notcol0[w] = a; p.g_notlast[w] = z;
     }
+    return MSW_OK;
+}
+
+// Geometry + the persistent env state.
+static int fill_params(EnvParams &p, const msw_env_desc *d, const msw_state *st, long long n)
+{
+    if (!st) return fail(MSW_ERR_NULL, "state is NULL");
+    if (!st->mines || !st->revealed || !st->meta) return fail(MSW_ERR_NULL, "state pointer is NULL");
+    if (((uintptr_t)st->meta & 15u) != 0) return fail(MSW_ERR_ALIGN, "state.meta must be 16-byte aligned");
+    const int rc = fill_geometry(p, d, n);
+    if (rc) return rc;
+    p.mines = st->mines; p.revealed = st->revealed; p.flags = st->flags;
+    p.meta = reinterpret_cast<int4 *>(st->meta);
     return MSW_OK;
 }
 
@@ -775,17 +785,18 @@ struct LaunchShape { int block, bpw, cap; };
 
 static inline const LaunchShape &launch_shape_cfg()
 {
-    static LaunchShape c = {0, 0, 0};
-    if (c.block == 0) {
+    static const LaunchShape c = [] {                 // initialised once, thread-safe (C++11 static init)
+        LaunchShape v;
         int blk = env_int("MSW_BLOCK", 32);
         if (blk < 32) blk = 32;
         if (blk > 256) blk = 256;
-        c.block = blk & ~31;
-        c.bpw = env_int("MSW_BPW", 3);
-        c.cap = env_int("MSW_CTAS_PER_SM", 8);
-        if (c.bpw < 0) c.bpw = 0;
-        if (c.cap < 0) c.cap = 0;
-    }
+        v.block = blk & ~31;
+        v.bpw = env_int("MSW_BPW", 3);
+        v.cap = env_int("MSW_CTAS_PER_SM", 8);
+        if (v.bpw < 0) v.bpw = 0;
+        if (v.cap < 0) v.cap = 0;
+        return v;
+    }();
     return c;
 }
 
@@ -815,12 +826,10 @@ static inline int grid_for(long long n, int *block_out)
 // 48 registers were measured slower and dropped.)
 static inline int variant()
 {
-    static int cached = -1;
-    if (cached < 0) {
+    static const int cached = [] {
         const char *e = getenv("MSW_VARIANT");
-        cached = e ? atoi(e) : 2;
-        if (cached != 0) cached = 2;
-    }
+        return (e && atoi(e) == 0) ? 0 : 2;
+    }();
     return cached;
 }
 
@@ -999,10 +1008,7 @@ extern "C" int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_
     if (!snap_mines || !snap_revealed || !snap_first || !idx) return fail(MSW_ERR_NULL, "msw_gather_encode: NULL pointer");
     if (rows_in < 1) return fail(MSW_ERR_BAD_SHAPE, "msw_gather_encode: rows_in=%lld", (long long)rows_in);
     GatherParams q;
-    msw_state fake = { const_cast<uint32_t *>(snap_mines), const_cast<uint32_t *>(snap_revealed),
-                       const_cast<uint32_t *>(snap_flags), reinterpret_cast<int32_t *>(const_cast<uint32_t *>(snap_mines)) };
-    if (((uintptr_t)snap_mines & 15u) != 0) return fail(MSW_ERR_ALIGN, "msw_gather_encode: snapshots must be 16-byte aligned");
-    int rc = fill_params(q.e, desc, &fake, m);
+    int rc = fill_geometry(q.e, desc, m);
     if (rc) return rc;
     if ((rc = set_encode_out(q.e, out, true))) return rc;
     q.e.flags = const_cast<uint32_t *>(snap_flags);           // encoder consults flags only when present

@@ -137,11 +137,10 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
     // 32 columns per CTA (one full 128-byte line per row).  16 columns -- twice the CTAs, so every SM
     // has work at N = 8,192 -- was measured slower (18.4 vs 14.3 us, half-line requests); it stays
     // selectable through MSW_GAE_COLS=16 for experiments.
-    static int forced = -1;
-    if (forced < 0) {
+    static const int forced = [] {
         const char *e = getenv("MSW_GAE_COLS");
-        forced = e ? atoi(e) : 0;
-    }
+        return e ? atoi(e) : 0;
+    }();
     const int cols = forced == 16 ? 16 : 32;
     const long long blocks = (N + cols - 1) / cols;
     if (blocks > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: N too large");

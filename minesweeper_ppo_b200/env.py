@@ -370,13 +370,17 @@ class VecMinesweeper:
         action -- exactly what `random_actions(step_index, valid_only, seed)` returns -- and steps."""
         if self.api != "torch":
             raise ValueError("step_random needs api='torch'")
-        return self.step(None, out=out, want_infos=want_infos,
-                         _rand=(1 if valid_only else 2, int(step_index), int(seed), actions_out))
+        return self._step_device(None, out, want_infos, (1 if valid_only else 2, int(step_index), int(seed), actions_out))
 
-    def step(self, actions, out: Optional[StepOut] = None, want_infos: bool = True, _rand=None):
+    def step(self, actions, out: Optional[StepOut] = None, want_infos: bool = True):
         """VecMinesweeper.step (env.py:479-511).  Returns (batch, rewards, dones, infos)."""
         if self.api == "numpy":
             return self._step_numpy(actions)
+        return self._step_device(actions, out, want_infos, None)
+
+    def _step_device(self, actions, out: Optional[StepOut], want_infos: bool, _rand):
+        """One msw_step launch on device tensors; `_rand` = (mode, step_index, seed, actions_out) selects
+        the built-in synthetic policy instead of `actions`."""
         n, dev = self.num_envs, self.device
         if _rand is None:
             if not isinstance(actions, torch.Tensor):
