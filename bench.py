@@ -389,7 +389,25 @@ def bench_gae(torch, m, dev):
     ms = float(np.median(cold))
     nbytes = 17 * T * N + 4 * N
     peak, _ = measured_peak_gbs()
-    return {"T": T, "N": N, "kernel_us": ms * 1e3, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
+    # CPU baseline: the reference's loop (buffers.py:85-94) on CPU tensors
+    r_c, v_c, d_c, lv_c = (x.cpu() for x in (buf.rewards.view(T, N), buf.values.view(T, N), buf.dones.view(T, N), last))
+    cpu_ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        adv_c = torch.zeros_like(v_c)
+        last_adv = torch.zeros((N,), dtype=torch.float32)
+        for t in reversed(range(T)):
+            nv = lv_c if t == T - 1 else v_c[t + 1]
+            nnt = 1.0 - d_c[t].float()
+            delta = r_c[t] + 0.995 * nv * nnt - v_c[t]
+            last_adv = delta + 0.995 * 0.95 * nnt * last_adv
+            adv_c[t] = last_adv
+        ret_c = adv_c + v_c
+        cpu_ms.append((time.perf_counter() - t0) * 1e3)
+    same = bool(torch.equal(adv_c, buf.advantages.view(T, N).cpu()) and torch.equal(ret_c, buf.returns.view(T, N).cpu()))
+    return {"T": T, "N": N, "kernel_us": ms * 1e3,
+            "cpu_reference_loop_ms": float(np.median(cpu_ms)), "cpu_threads": torch.get_num_threads(),
+            "bit_identical_to_cpu_loop": same, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
             "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "l2": "1 GB flush write before every timed launch (cold)",
             "back_to_back_us": warm_ms * 1e3,
             "note": "cold = inputs in HBM; back_to_back = 50 launches in a row (17.9 MB working set stays in L2, "
