@@ -164,6 +164,14 @@ int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_mines,
                       const uint8_t *snap_first, int64_t rows_in, const int64_t *idx,
                       int64_t m, const msw_encode_out *out, void *stream);
 
+/* rules.analyze_forced_modules (rules.py:206-259): the
+ * pairwise subset rule on ground-truth mines, for every env at once.  out_bits
+ * [n][wpb] receives the bitboard of "subset_reveal" cells (cells proven safe
+ * because two number cells with nested unknown-neighbour sets hold the same
+ * number of mines). */
+int msw_forced_subset(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                      uint32_t *out_bits, void *stream);
+
 /* Synthetic action source for benchmarks/tests: a
  * uniformly random unrevealed cell per env (valid_only=1; 0 if none) or a
  * uniformly random cell (valid_only=0).  Writes whichever of a32/a64 is

@@ -610,6 +610,107 @@ __global__ void __launch_bounds__(256) gather_encode_kernel(const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------
+// Eval-side analytics: rules.analyze_forced_modules (rules.py:206-259),
+// the pairwise subset rule on ground-truth mines.  For number cells a, b (revealed, count > 0) with
+// non-empty unknown-neighbour sets U(a), U(b) (unknown = not revealed; flags are ignored, :218):
+// if U(a) is a subset of U(b) and both contain the same number of mines, every cell of U(b) - U(a) is
+// safe.  A non-empty U(a) inside U(b) forces a and b within Chebyshev distance 2, so each number cell
+// only needs its 5x5 window instead of the reference's all-pairs loop.  One warp per board; the three
+// cell predicates are expanded to bytes in shared memory and each lane walks its cells with scalar
+// code (this runs at eval batch sizes; clarity over speed).
+// ---------------------------------------------------------------------------
+struct SubsetParams {
+    EnvParams e;
+    uint32_t *out;      // [n][wpb] bitboard of "subset_reveal" cells
+};
+
+__global__ void __launch_bounds__(128) subset_reveal_kernel(const __grid_constant__ SubsetParams q)
+{
+    extern __shared__ unsigned char s_raw[];
+    const EnvParams &p = q.e;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = p.H, W = p.W, HW = p.HW, wpb = p.wpb;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    unsigned char *s_unknown = s_raw + (size_t)warp * (3 * MSW_MAX_CELLS + 128);
+    unsigned char *s_mine = s_unknown + MSW_MAX_CELLS;
+    unsigned char *s_number = s_mine + MSW_MAX_CELLS;
+    uint32_t *s_res = reinterpret_cast<uint32_t *>(s_number + MSW_MAX_CELLS);
+    if (b >= p.n) return;
+    Geo g;
+    g.valid = p.g_valid[lane];
+    g.notcol0 = p.g_notcol0[lane];
+    g.notlast = p.g_notlast[lane];
+    uint32_t M = 0, R = 0;
+    if (lane < wpb) {
+        M = p.mines[b * wpb + lane];
+        R = p.revealed[b * wpb + lane];
+    }
+    const Planes pl = count_planes<0>(M, lane, W, g);
+    const uint32_t number = R & (pl.c0 | pl.c1 | pl.c2 | pl.c3) & g.valid;       // revealed & counts > 0 (:222)
+    const uint32_t unknown = ~R & g.valid;                                        // :218
+    for (int it = 0; it < wpb; ++it) {
+        const int cell = it * 32 + lane;
+        const uint32_t wu = __shfl_sync(FULL, unknown, it), wm = __shfl_sync(FULL, M, it), wn = __shfl_sync(FULL, number, it);
+        if (cell < HW) {
+            s_unknown[cell] = (wu >> lane) & 1u;
+            s_mine[cell] = (wm >> lane) & 1u;
+            s_number[cell] = (wn >> lane) & 1u;
+        }
+    }
+    s_res[lane] = 0u;
+    __syncwarp();
+
+    // unknown neighbours of (r, c): fills idx[] and returns the count; *mines = mines among them
+    auto unknown_nbrs = [&](int r, int c, int (&idx)[8], int *mines) {
+        int k = 0, m = 0;
+        for (int dr = -1; dr <= 1; ++dr)
+            for (int dc = -1; dc <= 1; ++dc) {
+                if (!dr && !dc) continue;
+                const int rr = r + dr, cc = c + dc;
+                if (rr < 0 || rr >= H || cc < 0 || cc >= W) continue;
+                const int u = rr * W + cc;
+                if (s_unknown[u]) {
+                    idx[k++] = u;
+                    m += s_mine[u];
+                }
+            }
+        *mines = m;
+        return k;
+    };
+    for (int a = lane; a < HW; a += 32) {
+        if (!s_number[a]) continue;
+        const int ra = a / W, ca = a % W;
+        int ua[8], ma;
+        const int na = unknown_nbrs(ra, ca, ua, &ma);
+        if (na == 0) continue;                                                    // :230-231
+        for (int br = -2; br <= 2; ++br)
+            for (int bc = -2; bc <= 2; ++bc) {
+                if (!br && !bc) continue;
+                const int rb = ra + br, cb = ca + bc;
+                if (rb < 0 || rb >= H || cb < 0 || cb >= W) continue;
+                const int bb = rb * W + cb;
+                if (!s_number[bb]) continue;
+                int ub[8], mb;
+                const int nb = unknown_nbrs(rb, cb, ub, &mb);
+                if (nb == 0 || ma != mb) continue;                                // :251, :255
+                bool subset = true;                                               // U(a) subset of U(b)?
+                for (int k = 0; k < na && subset; ++k) {
+                    const int dr = ua[k] / W - rb, dc = ua[k] % W - cb;
+                    subset = dr >= -1 && dr <= 1 && dc >= -1 && dc <= 1;
+                }
+                if (!subset) continue;
+                for (int k = 0; k < nb; ++k) {                                    // U(b) - U(a) is safe (:250-252)
+                    const int dr = ub[k] / W - ra, dc = ub[k] % W - ca;
+                    if (!(dr >= -1 && dr <= 1 && dc >= -1 && dc <= 1))
+                        atomicOr(&s_res[ub[k] >> 5], 1u << (ub[k] & 31));
+                }
+            }
+    }
+    __syncwarp();
+    if (lane < wpb) q.out[b * wpb + lane] = s_res[lane];
+}
+
 // Expansion of the bitboards into the reference's per-cell arrays for the
 // vec.envs[i] views (env.py:68-71, adjacent_counts per env.py:314-335).
 struct UnpackParams {
@@ -1023,6 +1124,21 @@ extern "C" int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_
         gather_encode_kernel<16, 256><<<(unsigned)blocks, 256, 0, st>>>(q);
     else
         gather_encode_kernel<0, 0><<<(unsigned)blocks, 256, 0, st>>>(q);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
+extern "C" int msw_forced_subset(const msw_env_desc *desc, const msw_state *st, int64_t n, uint32_t *out_bits,
+                                 void *stream)
+{
+    SubsetParams q;
+    int rc = fill_params(q.e, desc, st, n);
+    if (rc) return rc;
+    if (!out_bits) return fail(MSW_ERR_NULL, "msw_forced_subset: out_bits is NULL");
+    q.out = out_bits;
+    if (n == 0) return MSW_OK;
+    const size_t smem = 4 * (3 * (size_t)MSW_MAX_CELLS + 128);
+    subset_reveal_kernel<<<(unsigned)((n + 3) / 4), 128, smem, (cudaStream_t)stream>>>(q);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

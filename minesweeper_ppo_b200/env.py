@@ -336,6 +336,19 @@ class VecMinesweeper:
             self._cache["meta"] = self._meta.cpu().numpy()
         return self._cache
 
+    def forced_subset(self) -> np.ndarray:
+        """rules.analyze_forced_modules (rules.py:206-259) for every env in one launch: bool [n, HW]
+        of "subset_reveal" cells (cached until the next step / reset)."""
+        u = self._unpacked()
+        if "subset" not in u:
+            bits = torch.empty((self.num_envs, self.wpb), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.msw_forced_subset(C.byref(self._desc), C.byref(self._state), self.num_envs,
+                                                     bits.data_ptr(), self._stream()), "msw_forced_subset")
+            raw = bits.cpu().numpy().view(np.uint8).reshape(self.num_envs, -1)
+            u["subset"] = np.unpackbits(raw, axis=1, count=self.HW, bitorder="little").astype(bool)
+        return u["subset"]
+
     def random_actions(self, step_index: int, valid_only: bool = True, seed: int = 1,
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Synthetic action source: uniformly random unrevealed cell

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from .env import EnvConfig, VecMinesweeper
+from .rules import analyze_forced_modules
 
 
 def _auroc(labels: np.ndarray, scores: np.ndarray) -> float:
@@ -50,6 +51,7 @@ def evaluate_vec(model: torch.nn.Module, env_cfg: EnvConfig, episodes: int = 100
     HW = env_cfg.H * env_cfg.W
     remaining, wins, total_steps, total_progress, invalids = episodes, 0, 0, 0.0, 0
     probs, labels = [], []
+    forced_steps = forced_correct = guess_attempts = guess_success = 0
     while remaining > 0:
         batch_size = min(num_envs, remaining)
         finished = 0
@@ -74,6 +76,13 @@ def evaluate_vec(model: torch.nn.Module, env_cfg: EnvConfig, episodes: int = 100
                 if unknown.any():
                     probs.append(mine_prob[idx, 0][unknown])
                     labels.append(env.mine_mask[unknown].astype(np.float32))
+                # forced reveals by the subset rule (eval.py:362-379); one batched kernel per step
+                cell = int(actions[idx])
+                safe = not env.mine_mask[cell // env.W, cell % env.W]
+                if cell in analyze_forced_modules(env)["subset_reveal"]:
+                    forced_steps += 1; forced_correct += safe
+                else:
+                    guess_attempts += 1; guess_success += safe
             batch, rewards, dones, infos = vec.step(actions)
             step_counters += 1
             for i in range(num_envs):                                     # eval.py:405-428
@@ -95,5 +104,8 @@ def evaluate_vec(model: torch.nn.Module, env_cfg: EnvConfig, episodes: int = 100
         "win_rate": wins / max(1, episodes), "avg_steps": total_steps / max(1, episodes),
         "avg_progress": total_progress / max(1, episodes), "invalid_rate": invalids / max(1, total_steps),
         "belief_auroc": _auroc(y, p) if len(p) else float("nan"),
+        "forced_step_rate": forced_steps / max(1, forced_steps + guess_attempts),
+        "forced_step_accuracy": forced_correct / max(1, forced_steps),
+        "guess_success_rate": guess_success / max(1, guess_attempts),
         "wins": float(wins), "episodes": float(episodes),
     }

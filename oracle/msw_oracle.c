@@ -455,6 +455,56 @@ void orc_late_start(const orc_cfg *cfg, int64_t n, int64_t env_id_base, orc_stat
     }
 }
 
+/* ---- rules.analyze_forced_modules (rules.py:206-259), all pairs as the reference ------------ */
+void orc_forced_subset(const orc_cfg *cfg, int64_t n, const orc_state *st, uint8_t *out)
+{
+    const int H = cfg->H, W = cfg->W, HW = H * W;
+    static const int DR[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, DC[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    int16_t (*sets)[8] = malloc(sizeof(int16_t[8]) * (size_t)HW);
+    int *cnt = malloc(sizeof(int) * (size_t)HW), *mines = malloc(sizeof(int) * (size_t)HW);
+    int *keys = malloc(sizeof(int) * (size_t)HW);
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t *rev = st->revealed + i * HW, *mine = st->mine + i * HW, *counts = st->counts + i * HW;
+        uint8_t *o = out + i * HW;
+        memset(o, 0, (size_t)HW);
+        int nk = 0;
+        for (int a = 0; a < HW; ++a) {                              /* :222-235 */
+            if (!(rev[a] && counts[a] > 0)) continue;
+            int k = 0, m = 0;
+            for (int d = 0; d < 8; ++d) {
+                const int r = a / W + DR[d], c = a % W + DC[d];
+                if (r < 0 || r >= H || c < 0 || c >= W) continue;
+                if (!rev[r * W + c]) {
+                    sets[a][k++] = (int16_t)(r * W + c);
+                    m += mine[r * W + c] != 0;
+                }
+            }
+            if (k == 0) continue;
+            cnt[a] = k; mines[a] = m;
+            keys[nk++] = a;
+        }
+        for (int x = 0; x < nk; ++x)                                /* :237-257, both directions */
+            for (int y = 0; y < nk; ++y) {
+                if (x == y) continue;
+                const int a = keys[x], b = keys[y];
+                if (mines[a] != mines[b]) continue;
+                int subset = 1;
+                for (int k = 0; k < cnt[a] && subset; ++k) {
+                    int found = 0;
+                    for (int l = 0; l < cnt[b]; ++l) found |= sets[b][l] == sets[a][k];
+                    subset = found;
+                }
+                if (!subset) continue;
+                for (int l = 0; l < cnt[b]; ++l) {
+                    int in_a = 0;
+                    for (int k = 0; k < cnt[a]; ++k) in_a |= sets[a][k] == sets[b][l];
+                    if (!in_a) o[sets[b][l]] = 1;
+                }
+            }
+    }
+    free(sets); free(cnt); free(mines); free(keys);
+}
+
 /*
  * buffers.py:78-94.  torch evaluates, per t from T-1 down to 0 (all fp32,
  * Python scalars rounded to fp32 when they meet an fp32 tensor):

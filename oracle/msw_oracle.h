@@ -119,6 +119,10 @@ void orc_late_start(const orc_cfg *cfg, int64_t n, int64_t env_id_base, orc_stat
                     const uint8_t *sel, uint64_t late_seed, float prob, int min_hidden,
                     int max_hidden, int max_attempts, int max_extra_steps);
 
+/* rules.analyze_forced_modules (rules.py:206-259): out[i][cell] = 1 for the cells of
+ * "subset_reveal" of env i.  Restated with the reference's all-pairs loop. */
+void orc_forced_subset(const orc_cfg *cfg, int64_t n, const orc_state *st, uint8_t *out);
+
 /* buffers.py:78-94 in IEEE fp32 without contraction. */
 void orc_gae(int64_t T, int64_t N, const float *rewards, const float *values,
              const uint8_t *dones, const float *last_values, float gamma_f32,

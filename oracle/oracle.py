@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.orc_vec_encode.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State)] + [C.c_void_p] * 4 + [C.c_int]
         L.orc_late_start.argtypes = [C.POINTER(_Cfg), C.c_int64, C.c_int64, C.POINTER(_State), C.c_void_p, C.c_uint64,
                                      C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_forced_subset.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State), C.c_void_p]
         L.orc_gae.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 2
         _lib = L
     return _lib
@@ -228,6 +229,12 @@ class OracleVecEnv:
         self._late(None, obs, mask, lab, val)
         self.mine_labels, self.mine_valid = lab, (None if val is None else val.view(bool))
         return {"obs": obs, "action_mask": mask.view(bool)}
+
+    def forced_subset(self) -> np.ndarray:
+        """rules.analyze_forced_modules for every env: bool [n, HW] of "subset_reveal" cells."""
+        out = np.zeros((self.num_envs, self.HW), np.uint8)
+        lib().orc_forced_subset(C.byref(self._ccfg), self.num_envs, C.byref(self._st), out.ctypes.data)
+        return out.astype(bool)
 
     def _late(self, sel, obs, mask, lab, val):
         """env.py:406-414: late start on the envs just reset, then observe them again."""

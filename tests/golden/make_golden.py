@@ -348,7 +348,46 @@ def run_late_start_stats():
     json.dump(out, open(os.path.join(OUT, "late_start_stats.json"), "w"), indent=1)
 
 
+def run_forced_subset_case():
+    """rules.analyze_forced_modules (rules.py:206-259) on mid-game states: late start + random valid
+    play give boards with long frontiers; every env is analysed at several time points."""
+    from minesweeper.rules import analyze_forced_modules
+    out = {"names": []}
+    cases = {
+        "16x16x40": (EnvConfig(H=16, W=16, mine_count=40, step_penalty=1e-4), dict(prob=0.8, min_hidden=20, max_hidden=150), 48),
+        "8x8x10": (EnvConfig(), dict(prob=0.8, min_hidden=4, max_hidden=40), 64),
+        "16x30x99": (EnvConfig(H=16, W=30, mine_count=99), dict(prob=0.8, min_hidden=40, max_hidden=300), 24),
+        "5x7x6": (EnvConfig(H=5, W=7, mine_count=6), dict(prob=0.5, min_hidden=3, max_hidden=20), 64),
+    }
+    for name, (cfg, ls, N) in cases.items():
+        HW = cfg.H * cfg.W
+        vec = VecMinesweeper(N, cfg, seed=21, late_start_cfg=ls, late_start_seed=22)
+        b = vec.reset()
+        rng = np.random.default_rng(2)
+        revs, mines, subs = [], [], []
+        hits = 0
+        for t in range(6):
+            for e in vec.envs:
+                sr = analyze_forced_modules(e)["subset_reveal"]
+                m = np.zeros(HW, bool); m[list(sr)] = True
+                revs.append(e.revealed.reshape(-1).copy()); mines.append(e.mine_mask.reshape(-1).copy()); subs.append(m)
+                hits += len(sr)
+            mask = b["action_mask"]
+            s_ = rng.random(mask.shape); s_[~mask] = -1
+            b, _, _, _ = vec.step(s_.argmax(1).astype(np.int32))
+        out["names"].append(name)
+        out[f"{name}_cfg"] = np.array([cfg.H, cfg.W, cfg.mine_count])
+        for key, arr in (("rev", revs), ("mine", mines), ("subset", subs)):
+            out[f"{name}_{key}"] = np.packbits(np.stack(arr).astype(np.uint8), axis=1, bitorder="little")
+        print(f"forced_subset {name}: {len(revs)} states, {hits} subset_reveal cells")
+    out["names"] = np.array(out["names"])
+    np.savez_compressed(os.path.join(OUT, "forced_subset.npz"), **out)
+
+
 def main():
+    if "--subset-only" in sys.argv:
+        run_forced_subset_case()
+        return
     if "--late-only" in sys.argv:
         run_late_start_stats()
         return
@@ -369,6 +408,7 @@ def main():
     run_gae_cases()
     run_rollout_case()
     run_late_start_stats()
+    run_forced_subset_case()
 
 
 if __name__ == "__main__":
