@@ -257,14 +257,15 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         v.reset()
         for t in range(Wm):
             v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
+        rows = [acts_host[Wm + t] for t in range(steps)]
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         done_count = 0
-        for t in range(steps):
-            pin = v.step_host(acts_host[Wm + t], copy_obs=copy_obs, copy_infos=False)
-            done_count += int(pin["done"].sum())          # the host really reads the result
+        for a in rows:
+            pin = v.step_host(a, copy_obs=copy_obs, copy_infos=False)
+            done_count += int(np.count_nonzero(pin["done"].numpy()))   # the host really reads the result
         e1.record()
         barrier()
         wall = time.perf_counter() - t0

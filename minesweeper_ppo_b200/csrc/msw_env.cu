@@ -19,6 +19,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef MSW_HOST_MODE_DEFAULT
+#define MSW_HOST_MODE_DEFAULT 0
+#endif
+
 namespace msw {
 
 struct EnvParams {
@@ -1018,6 +1022,28 @@ extern "C" int msw_step(const msw_env_desc *desc, const msw_state *st, const msw
     return launch_env<MODE_STEP>(p, (cudaStream_t)stream);
 }
 
+// Transfer plan of msw_step_host.  bit 0: the kernel reads the actions straight from the pinned
+// host buffer (no H2D copy node); bit 1: the per-env scalar outputs are written by the kernel
+// straight into the pinned host buffers (no D2H copy nodes).  MSW_HOST_MODE overrides the default
+// for measurements (tools/e2e_probe.sh).
+static int host_mode()
+{
+    static const int mode = [] {
+        const char *e = getenv("MSW_HOST_MODE");
+        return e ? atoi(e) : MSW_HOST_MODE_DEFAULT;
+    }();
+    return mode;
+}
+
+static int mapped_ptr(void **dev, const void *host, const char *what)
+{
+    if (cudaHostGetDevicePointer(dev, const_cast<void *>(host), 0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MSW_ERR_ARG, what);
+    }
+    return MSW_OK;
+}
+
 extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, const msw_step_io *io,
                              const int32_t *h_actions32, const msw_host_out *h, int64_t n, void *stream)
 {
@@ -1027,24 +1053,56 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     if (!h_actions32 || !io->actions32) return fail(MSW_ERR_NULL, "msw_step_host needs h_actions32 and io->actions32 staging");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)n, HW = (size_t)p.HW;
-    MSW_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(io->actions32), h_actions32, N * 4, cudaMemcpyHostToDevice, s));
+    const int mode = host_mode();
+
+    struct Copy { void *dst; const void *src; size_t bytes; };
+    Copy copies[8];
+    int nc = 0;
+    // Queue a device->host copy; a copy that continues the previous one on both sides is merged into it
+    // (the Python mirror lays reward|done|... out back to back, so the scalars travel as one DMA).
+    auto d2h = [&](void *dst, const void *src, size_t bytes) {
+        if (nc && (const char *)copies[nc - 1].src + copies[nc - 1].bytes == (const char *)src &&
+            (char *)copies[nc - 1].dst + copies[nc - 1].bytes == (char *)dst)
+            copies[nc - 1].bytes += bytes;
+        else
+            copies[nc++] = {dst, src, bytes};
+    };
+#define MSW_HOST_SCALAR(field, dev, type, bytes)                                                           \
+    if (h && h->field) {                                                                                   \
+        if (!(dev)) return fail(MSW_ERR_NULL, "host output " #field " requested without device staging"); \
+        if (mode & 2) {                                                                                    \
+            void *m = nullptr;                                                                             \
+            if ((rc = mapped_ptr(&m, h->field, "host output " #field " is not mapped pinned memory"))) return rc; \
+            dev = static_cast<type *>(m);                                                                  \
+        } else                                                                                             \
+            d2h(h->field, dev, bytes);                                                                     \
+    }
+    if (h && h->obs) {
+        if (!p.obs) return fail(MSW_ERR_NULL, "host output obs requested without device staging");
+        d2h(h->obs, p.obs, N * MSW_OBS_CHANNELS * HW * 4);
+    }
+    if (h && h->mask) {
+        if (!p.mask) return fail(MSW_ERR_NULL, "host output mask requested without device staging");
+        d2h(h->mask, p.mask, N * HW);
+    }
+    MSW_HOST_SCALAR(reward, p.reward, float, N * 4)
+    MSW_HOST_SCALAR(done, p.done, uint8_t, N)
+    MSW_HOST_SCALAR(outcome, p.outcome, int8_t, N)
+    MSW_HOST_SCALAR(new_reveals, p.new_reveals, int32_t, N * 4)
+    MSW_HOST_SCALAR(step, p.step, int32_t, N * 4)
+    MSW_HOST_SCALAR(revealed_count, p.rcount, int32_t, N * 4)
+#undef MSW_HOST_SCALAR
+
+    if (mode & 1) {
+        void *m = nullptr;
+        if ((rc = mapped_ptr(&m, h_actions32, "h_actions32 is not mapped pinned memory"))) return rc;
+        p.a32 = static_cast<const int32_t *>(m);
+    } else {
+        MSW_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(io->actions32), h_actions32, N * 4, cudaMemcpyHostToDevice, s));
+    }
     if ((rc = launch_env<MODE_STEP>(p, s))) return rc;
-    if (h) {
-#define MSW_D2H(dst, src, bytes)                                                              \
-    if (dst) {                                                                                \
-        if (!(src)) return fail(MSW_ERR_NULL, "host output " #dst " requested without device staging"); \
-        MSW_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));            \
-    }
-        MSW_D2H(h->obs, p.obs, N * MSW_OBS_CHANNELS * HW * 4)
-        MSW_D2H(h->mask, p.mask, N * HW)
-        MSW_D2H(h->reward, p.reward, N * 4)
-        MSW_D2H(h->done, p.done, N)
-        MSW_D2H(h->outcome, p.outcome, N)
-        MSW_D2H(h->new_reveals, p.new_reveals, N * 4)
-        MSW_D2H(h->step, p.step, N * 4)
-        MSW_D2H(h->revealed_count, p.rcount, N * 4)
-#undef MSW_D2H
-    }
+    for (int i = 0; i < nc; ++i)
+        MSW_CUDA_TRY(cudaMemcpyAsync(copies[i].dst, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToHost, s));
     MSW_CUDA_TRY(cudaStreamSynchronize(s));
     return MSW_OK;
 }

@@ -13,9 +13,13 @@
 // columns is one 128-byte line.  A CTA owns 16 or 32 columns: all 8 warps stream
 // the [TC x COLS] tiles of rewards / values / dones into shared memory with
 // coalesced loads (the only way to get enough bytes in flight when N is a few
-// thousand columns), one warp walks the chains out of shared memory, and all
-// warps write advantages / returns back coalesced.  HBM-bound in principle (17 B per
-// transition) but latency-bound at the reference's sizes.
+// thousand columns).  Only `last` carries a dependency from t+1 to t -- next_value is
+// values[t+1], plain data -- so all 256 threads then form delta[t] for their own
+// elements in place, and the one warp that walks the chains does just
+// FSEL / FMUL / FADD per step out of shared memory.  All warps write advantages /
+// returns back coalesced.  HBM-bound in principle (17 B per transition) but
+// latency-bound at the reference's sizes: forming delta inside the serial walk instead
+// takes the same 14.3 us (A/B in one process, round 1), i.e. the walk is not the long pole.
 #include "../../include/msw_b200.h"
 #include "msw_error.h"
 
@@ -37,9 +41,10 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
            float *__restrict__ adv, float *__restrict__ ret, long long T, long long N,
            float gamma, float gamma_lam, int prescaled)
 {
-    __shared__ float s_r[GAE_TC][COLS];     // rewards in, advantages out
+    __shared__ float s_r[GAE_TC][COLS];     // rewards in, then delta, then advantages
     __shared__ float s_v[GAE_TC][COLS];
     __shared__ uint8_t s_d[GAE_TC][COLS];
+    __shared__ float s_gvn[COLS];           // gamma * value of the row after this chunk's last one
     constexpr int RPP = GAE_THREADS / COLS;       // rows per pass of the whole CTA
     constexpr int RPT = GAE_TC / RPP;             // rows per thread and chunk
 
@@ -50,13 +55,15 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
     const bool chain = threadIdx.x < COLS;        // warp 0, first COLS lanes
 
     float last = 0.0f;                                          // buffers.py:86
-    float next_value = (chain && in) ? last_values[col] : 0.0f; // buffers.py:88 (t == T-1)
-    bool scaled = prescaled != 0;       // last_values already is gamma*last_value (fp16 bootstrap)
+    if (chain) {                                                // buffers.py:88 (t == T-1)
+        const float lv = in ? last_values[col] : 0.0f;
+        // prescaled: last_values already is gamma*last_value (fp16 bootstrap)
+        s_gvn[c] = prescaled ? lv : __fmul_rn(gamma, lv);
+    }
 
     for (long long t_hi = T; t_hi > 0; t_hi -= GAE_TC) {
         const long long t_lo = t_hi > GAE_TC ? t_hi - GAE_TC : 0;
         const int rows = (int)(t_hi - t_lo);
-        __syncthreads();
         // ---- load: every thread issues all of its (up to 3*RPT) loads before the first use, so a
         // CTA has its whole tile in flight at once (the kernel is latency-, not bandwidth-bound)
         {
@@ -80,28 +87,36 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
             }
         }
         __syncthreads();
-        // ---- chain: 8 rows per batch read into registers ahead of the dependent arithmetic
+        // ---- delta[t] = (r[t] + (gamma * v[t+1]) * nnt[t]) - v[t] for the thread's own elements
+        // (buffers.py:88-90); each thread rewrites only the s_r entries it stored itself
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int i = rr + k * RPP;
+            if (i < rows) {
+                const float gv = i + 1 < rows ? __fmul_rn(gamma, s_v[i + 1][c]) : s_gvn[c];
+                const float nn = s_d[i][c] ? 0.0f : 1.0f;
+                s_r[i][c] = __fsub_rn(__fadd_rn(s_r[i][c], __fmul_rn(gv, nn)), s_v[i][c]);
+            }
+        }
+        __syncthreads();
+        // ---- chain: last = delta + ((gamma*lam) * nnt) * last (buffers.py:91), 8 rows per batch read
+        // into registers ahead of the dependent arithmetic
         if (chain) {
+            s_gvn[c] = __fmul_rn(gamma, s_v[0][c]);     // for the chunk before this one in time
             for (int hi = rows; hi > 0; hi -= 8) {
-                float r[8], v[8], nn[8];
+                float dl[8], gl[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int i = hi - 1 - k;
-                    const bool ok = i >= 0;
-                    r[k] = ok ? s_r[ok ? i : 0][c] : 0.0f;
-                    v[k] = ok ? s_v[ok ? i : 0][c] : 0.0f;
-                    nn[k] = (ok && s_d[ok ? i : 0][c]) ? 0.0f : 1.0f;
+                    const int i = hi - 1 - k >= 0 ? hi - 1 - k : 0;
+                    dl[k] = s_r[i][c];
+                    gl[k] = s_d[i][c] ? 0.0f : gamma_lam;      // == gamma_lam * nnt exactly
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int i = hi - 1 - k;
                     if (i >= 0) {
-                        const float gv = scaled ? next_value : __fmul_rn(gamma, next_value);
-                        scaled = false;
-                        const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(gv, nn[k])), v[k]);
-                        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lam, nn[k]), last));
+                        last = __fadd_rn(dl[k], __fmul_rn(gl[k], last));
                         s_r[i][c] = last;
-                        next_value = v[k];
                     }
                 }
             }
@@ -119,6 +134,7 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
                 }
             }
         }
+        __syncthreads();        // the next chunk overwrites the tiles and reads s_gvn
     }
 }
 
@@ -144,14 +160,13 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
     const int cols = forced == 16 ? 16 : 32;
     const long long blocks = (N + cols - 1) / cols;
     if (blocks > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: N too large");
-    if (cols == 16)
-        gae_kernel<16><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(
-            rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32,
-            (int)last_values_prescaled);
-    else
-        gae_kernel<32><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(
-            rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32,
-            (int)last_values_prescaled);
+#define MSW_GAE_LAUNCH(C)                                                                           \
+    gae_kernel<C><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(                  \
+        rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32, \
+        (int)last_values_prescaled)
+    if (cols == 16) MSW_GAE_LAUNCH(16);
+    else            MSW_GAE_LAUNCH(32);
+#undef MSW_GAE_LAUNCH
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }

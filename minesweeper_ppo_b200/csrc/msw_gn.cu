@@ -40,6 +40,17 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Chan et al. update of (count, mean, M2) a <- a (+) b; empty sides pass the other through.
+__device__ __forceinline__ void chan_merge(float &na, float &ma, float &qa, float nb, float mb, float qb)
+{
+    if (nb > 0.0f) {
+        const float nn = na + nb, delta = mb - ma, w = __fdividef(nb, nn);
+        ma = fmaf(delta, w, ma);
+        qa += qb + delta * delta * (na * w);
+        na = nn;
+    }
+}
+
 struct GnParams {
     const __half *x;        // [n][HW][C]
     const float *cbias;     // nullable [C]: bias of the convolution that produced x, added before the norm
@@ -126,25 +137,33 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
         s_part[256 + tid] = tmean;
         s_part[512 + tid] = tm2;
         __syncthreads();
-        if (tid < p.G) {
-            const int j0 = tid * (p.cpg / 8), j1 = j0 + p.cpg / 8;
-            float na = 0.0f, ma = 0.0f, qa = 0.0f;
-            for (int r = 0; r < p.PPB; ++r)
-                for (int jj = j0; jj < j1; ++jj) {
-                    const int t = r * p.CB + jj;
-                    const float nb = s_part[t];
-                    if (nb > 0.0f) {
-                        const float nn = na + nb, delta = s_part[256 + t] - ma;
-                        ma += delta * (nb / nn);
-                        qa += s_part[512 + t] + delta * delta * (na * nb / nn);
-                        na = nn;
+        // One warp per group: lane l folds partials l, l+32, ... of the group in index order, then a
+        // shuffle tree merges the 32 lanes (a fixed order again, ~10x shorter than one thread walking
+        // all PPB * cpg/8 partials while the CTA waits at the barrier).
+        {
+            const int cpc = p.cpg / 8, per_group = p.PPB * cpc, lane = tid & 31;
+            for (int gg = tid >> 5; gg < p.G; gg += 8) {
+                float na = 0.0f, ma = 0.0f, qa = 0.0f;
+                for (int q = lane; q < per_group; q += 32) {
+                    const int t = (q / cpc) * p.CB + gg * cpc + q % cpc;
+                    chan_merge(na, ma, qa, s_part[t], s_part[256 + t], s_part[512 + t]);
+                }
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float nb = __shfl_down_sync(0xffffffffu, na, off);
+                    const float mb = __shfl_down_sync(0xffffffffu, ma, off);
+                    const float qb = __shfl_down_sync(0xffffffffu, qa, off);
+                    chan_merge(na, ma, qa, nb, mb, qb);
+                }
+                if (lane == 0) {
+                    const float rstd = rsqrtf(qa * p.inv_count + p.eps);   // biased variance, eps as torch
+                    s_sum[gg] = ma;                                         // group mean of (x + conv_bias)
+                    s_sq[gg] = rstd;
+                    if (p.save_mean) {
+                        p.save_mean[n * p.G + gg] = ma;
+                        p.save_rstd[n * p.G + gg] = rstd;
                     }
                 }
-            s_sum[tid] = ma;                                        // group mean of (x + conv_bias)
-            s_sq[tid] = rsqrtf(qa * p.inv_count + p.eps);           // group rstd (biased variance, eps as torch)
-            if (p.save_mean) {
-                p.save_mean[n * p.G + tid] = ma;
-                p.save_rstd[n * p.G + tid] = s_sq[tid];
             }
         }
         __syncthreads();

@@ -454,9 +454,26 @@ class VecMinesweeper:
                 "outcome": ((n,), torch.int8), "new_reveals": ((n,), torch.int32), "step": ((n,), torch.int32),
                 "revealed_count": ((n,), torch.int32),
             }
+            # The per-env scalars sit back to back (reward | done | outcome | pad | new_reveals | step |
+            # revealed_count) in ONE pinned and ONE device allocation, in the order msw_step_host queues
+            # its copies, so they travel as a single DMA.
+            scalars = ("reward", "done", "outcome", "new_reveals", "step", "revealed_count")
+            offs, off = {}, 0
+            for k in scalars:
+                shape, dt = spec[k]
+                off = (off + dt.itemsize - 1) // dt.itemsize * dt.itemsize
+                offs[k] = off
+                off += n * dt.itemsize
+            pin_blob = torch.empty((off,), dtype=torch.uint8).pin_memory()
+            dev_blob = torch.empty((off,), dtype=torch.uint8, device=dev)
             for k, (shape, dt) in spec.items():
-                self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
-                self._staging["h_" + k] = torch.empty(shape, dtype=dt, device=dev)
+                if k in offs:
+                    nb = n * dt.itemsize
+                    self._pinned[k] = pin_blob[offs[k]:offs[k] + nb].view(dt)
+                    self._staging["h_" + k] = dev_blob[offs[k]:offs[k] + nb].view(dt)
+                else:
+                    self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
+                    self._staging["h_" + k] = torch.empty(shape, dtype=dt, device=dev)
             if self.aux_maps:
                 self._staging["h_labels"] = torch.empty((n, H, W), dtype=torch.float32, device=dev)
                 self._staging["h_valid"] = torch.empty((n, H, W), dtype=torch.bool, device=dev)
@@ -494,17 +511,16 @@ class VecMinesweeper:
             if copy_infos:
                 h.outcome, h.new_reveals = pin["outcome"].data_ptr(), pin["new_reveals"].data_ptr()
                 h.step, h.revealed_count = pin["step"].data_ptr(), pin["revealed_count"].data_ptr()
-            prepared = self._host_calls[key] = (io, h)
-        io, h = prepared
+            prepared = self._host_calls[key] = (io, h, C.byref(self._desc), C.byref(self._state), C.byref(io),
+                                                C.byref(h))
+        io, h, r_desc, r_state, r_io, r_h = prepared
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
         if torch.cuda.current_device() == self.device.index:
-            rc = self._L.msw_step_host(C.byref(self._desc), C.byref(self._state), C.byref(io), ap, C.byref(h), n,
-                                       self._stream())
+            rc = self._L.msw_step_host(r_desc, r_state, r_io, ap, r_h, n, self._stream())
         else:
             with torch.cuda.device(self.device):
-                rc = self._L.msw_step_host(C.byref(self._desc), C.byref(self._state), C.byref(io), ap, C.byref(h), n,
-                                           self._stream())
+                rc = self._L.msw_step_host(r_desc, r_state, r_io, ap, r_h, n, self._stream())
         if rc:
             _lib.check(rc, "msw_step_host")
         self._inject = None
