@@ -216,13 +216,28 @@ int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *m
  * input) and/or y32 (fp32 NHWC, the residual stream) are written.  Needs
  * C % 8 == 0 and (C/G) % 8 == 0; drop_p > 0 applies a Dropout2d channel mask
  * keyed by (seed, call_id [+ *epoch in the high word], sample, channel) and is
- * only allowed without res32. */
+ * only allowed without res32.  pool32 (nullable, fp32 [n][C]) receives the
+ * mean over HW of the fp32 output -- the AdaptiveAvgPool2d(1) that opens the
+ * value head (cnn_residual.py:65) -- so the last block need not write y32. */
 int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
                const float *gamma, const float *beta,
                void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
                float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
                const uint32_t *epoch, float *save_mean, float *save_rstd,
-               uint8_t *save_mask, void *stream);
+               uint8_t *save_mask, float *pool32, void *stream);
+
+/* Both per-cell heads of CNNResidualPolicy (cnn_residual.py:57-62, 73-77,
+ * 87-94: 1x1 conv C->C, ReLU, 1x1 conv C->1, for the policy and for the mine
+ * belief) in one launch over the fp16 NHWC trunk activation a16 [rows][C],
+ * rows = n*H*W.  w1 [2C][C] / b1 [2C]: first-layer weights and biases, policy
+ * units first; w2 [2C] / b2 [2]: second-layer weights and biases; all fp16, as
+ * the fp16 autocast of train_rl.py:222 casts them.  fp32 accumulation, hidden
+ * activations rounded to fp16 before the ReLU as the reference's conv output
+ * is.  Writes fp16 out_policy [rows] (= logits [n][H*W]) and out_mine [rows]
+ * (= mine logits [n][1][H][W]).  C in {32, 64, 96, 128}. */
+int msw_cell_heads(const void *a16, const void *w1, const void *b1, const void *w2,
+                   const void *b2, void *out_policy, void *out_mine, int64_t rows,
+                   int32_t C, void *stream);
 
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and

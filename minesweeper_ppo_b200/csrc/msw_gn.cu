@@ -59,6 +59,7 @@ struct GnParams {
     __half *y16;            // nullable [n][HW][C]
     float *y32;             // nullable [n][HW][C]
     int HW, C, G, cpg, CB, PPB;
+    unsigned tile_bytes;
     float eps, inv_count, drop_p, drop_scale;
     int relu;
     uint32_t k0, k1, call_lo, call_hi;
@@ -66,6 +67,7 @@ struct GnParams {
     // training forward: what msw_gn_act_bwd needs (all nullable)
     float *save_mean, *save_rstd;   // [n][G] statistics of (x + conv_bias)
     uint8_t *save_mask;             // [n][HW][C/8]: bit k of a byte = output channel 8j+k is "on" (ReLU active, not dropped)
+    float *pool;                    // nullable [n][C]: mean over HW of the fp32 output (AdaptiveAvgPool2d(1) of the value head)
 };
 
 __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long long n_samples)
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
     // compute + store) was measured SLOWER (5.0 vs 4.0 ms per forward): it halves the resident warps,
     // and the latency-bound statistics / normalise phases need them more than the loads need overlap.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t tile_bytes = (size_t)p.HW * p.C * 2;
+    const size_t tile_bytes = p.tile_bytes;       // the fp16 sample, or the pooling scratch if that is larger
     float *s_sum = reinterpret_cast<float *>(smem_raw + tile_bytes);              // [G]
     float *s_sq = s_sum + p.G;
     float *s_part = s_sq + p.G;                                                   // [3][256] per-thread partials
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
             }
         }
         __syncthreads();
+        float psum[8];
         if (active) {
             const float mean = s_sum[g], rstd = s_sq[g];
             // per-channel affine folded with the statistics, and the Dropout2d channel mask
@@ -195,6 +198,8 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
             const float4 *__restrict__ res = p.res ? reinterpret_cast<const float4 *>(p.res) + 2 * base : nullptr;
             uint4 *__restrict__ y16 = p.y16 ? reinterpret_cast<uint4 *>(p.y16) + base : nullptr;
             float4 *__restrict__ y32 = p.y32 ? reinterpret_cast<float4 *>(p.y32) + 2 * base : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) psum[k] = 0.0f;
 #pragma unroll 4
             for (int r = r0; r < p.HW; r += p.PPB) {
                 const int idx = r * p.CB + j;
@@ -222,6 +227,10 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
 #pragma unroll
                     for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.0f);
                 }
+                if (p.pool) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) psum[k] += o[k];
+                }
                 if (y32) {
                     y32[2 * idx] = make_float4(o[0], o[1], o[2], o[3]);
                     y32[2 * idx + 1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -233,6 +242,22 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
                     for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
                     y16[idx] = out;
                 }
+            }
+        }
+        if (p.pool) {
+            // per-channel mean of the output: the thread partials go through the (now dead) tile and are
+            // summed over the PPB pixel slots in index order -- fixed order, no float atomics
+            __syncthreads();
+            float *s_pool = reinterpret_cast<float *>(smem_raw);                      // [PPB][C]
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s_pool[r0 * p.C + j * 8 + k] = psum[k];
+            }
+            __syncthreads();
+            for (int c = tid; c < p.C; c += 256) {
+                float t = 0.0f;
+                for (int r = 0; r < p.PPB; ++r) t += s_pool[r * p.C + c];
+                p.pool[n * p.C + c] = t / (float)p.HW;
             }
         }
     }
@@ -408,10 +433,10 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
                           const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
                           float drop_p, uint64_t seed, uint64_t call_id, const uint32_t *epoch, float *save_mean,
-                          float *save_rstd, uint8_t *save_mask, void *stream)
+                          float *save_rstd, uint8_t *save_mask, float *pool32, void *stream)
 {
     using namespace msw;
-    if (!x16 || !gamma || !beta || (!y16 && !y32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
+    if (!x16 || !gamma || !beta || (!y16 && !y32 && !pool32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
     if (n < 0 || HW < 1 || C < 8 || G < 1 || C % G != 0 || C % 8 != 0 || (C / G) % 8 != 0 || C / 8 > 256 || 2 * G > 256)
         return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: need C %% 8 == 0, (C/G) %% 8 == 0 (C=%d G=%d HW=%d)", C, G, HW);
     if (drop_p < 0.0f || drop_p >= 1.0f) return fail(MSW_ERR_ARG, "msw_gn_act: drop_p=%f", drop_p);
@@ -419,7 +444,9 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     if ((((uintptr_t)x16 | (uintptr_t)res32 | (uintptr_t)y16 | (uintptr_t)y32) & 15u) != 0)
         return fail(MSW_ERR_ALIGN, "msw_gn_act: tensors must be 16-byte aligned");
     if (n == 0) return MSW_OK;
-    const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 3 * 256) * sizeof(float);
+    size_t tile_bytes = (size_t)HW * C * 2;
+    if (pool32 && (size_t)(256 / (C / 8)) * C * sizeof(float) > tile_bytes) tile_bytes = (size_t)(256 / (C / 8)) * C * sizeof(float);
+    const size_t smem = tile_bytes + (2 * (size_t)G + 3 * 256) * sizeof(float);
     if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: sample of %zu bytes does not fit shared memory", smem);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -436,6 +463,8 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
     p.call_lo = (uint32_t)call_id; p.call_hi = (uint32_t)(call_id >> 32);
     p.epoch = epoch;
+    p.pool = pool32;
+    p.tile_bytes = (unsigned)tile_bytes;
     if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))
         return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;

@@ -22,9 +22,11 @@ from .policy import CNNResidualPolicy
 def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[torch.Tensor] = None,
            res32: Optional[torch.Tensor] = None, relu: bool = True,
            drop_p: float = 0.0, want16: bool = True, want32: bool = False, seed: int = 0, call_id: int = 0,
-           epoch: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+           epoch: Optional[torch.Tensor] = None, pool32: Optional[torch.Tensor] = None
+           ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """x16: fp16 [N,C,H,W] in channels_last memory format (conv output, bias NOT applied when
-    `conv_bias` -- fp32 [C] -- is given).  Returns (y16, y32) with the same logical shape / memory format."""
+    `conv_bias` -- fp32 [C] -- is given).  Returns (y16, y32) with the same logical shape / memory format;
+    `pool32` (fp32 [N,C], optional) receives the spatial mean of the fp32 output."""
     L = _lib.load()
     if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("gn_act: x must be fp16 channels_last")
@@ -33,6 +35,8 @@ def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[t
     y16 = torch.empty_like(x16, memory_format=torch.channels_last) if want16 else None
     y32 = (torch.empty((N, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
            if want32 else None)
+    if pool32 is not None and (pool32.dtype != torch.float32 or tuple(pool32.shape) != (N, C) or not pool32.is_contiguous()):
+        raise ValueError("gn_act: pool32 must be contiguous fp32 [N, C]")
     if res32 is not None and (res32.dtype != torch.float32 or tuple(res32.shape) != (N, C, H, W)
                               or not res32.is_contiguous(memory_format=torch.channels_last)):
         raise ValueError("gn_act: residual must be fp32 channels_last of the same shape")
@@ -43,9 +47,26 @@ def gn_act(x16: torch.Tensor, norm: torch.nn.GroupNorm, *, conv_bias: Optional[t
                           None if y32 is None else y32.data_ptr(), N, H * W, C, norm.num_groups, float(norm.eps),
                           int(relu), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFFFFFFFFFF,
                           None if epoch is None else epoch.data_ptr(), None, None, None,
-                          torch.cuda.current_stream(dev).cuda_stream)
+                          None if pool32 is None else pool32.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "msw_gn_act")
     return y16, y32
+
+
+def cell_heads(rows16: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """msw_cell_heads: rows16 fp16 [R, C] (NHWC activation viewed as rows) -> (policy logit, mine logit),
+    fp16 [R] each; w1 [2C, C], b1 [2C], w2 [2C], b2 [2] fp16."""
+    L = _lib.load()
+    R, C = rows16.shape
+    if rows16.dtype != torch.float16 or not rows16.is_contiguous():
+        raise ValueError("cell_heads: rows must be contiguous fp16 [R, C]")
+    dev = rows16.device
+    out = torch.empty((2, R), dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.msw_cell_heads(rows16.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                              out[0].data_ptr(), out[1].data_ptr(), R, C, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "msw_cell_heads")
+    return out[0], out[1]
 
 
 class FusedRolloutForward:
@@ -90,11 +111,11 @@ class FusedRolloutForward:
             dev = p0.weight.device
             self.stem = conv3(m.stem[0])
             self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
-            # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation;
-            # their first layers share one GEMM, their second layers one block-diagonal GEMM
+            # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation:
+            # one msw_cell_heads launch, the hidden layer never reaches HBM
             self.head1 = lin(2 * C, C, dev)
-            self.head2 = lin(2, 2 * C, dev)
-            self.head2[0].zero_()
+            self.head2 = (torch.empty((2 * C,), dtype=torch.float16, device=dev),       # policy w2 | mine w2
+                          torch.empty((2,), dtype=torch.float16, device=dev))
             self.value = [lin(m.value_head[i].out_features, m.value_head[i].in_features, dev) for i in (2, 4, 6)]
             self._w = [self.stem]
 
@@ -108,7 +129,7 @@ class FusedRolloutForward:
             put3(d2, b.conv2)
         self.head1[0][:C].copy_(p0.weight.reshape(C, C)); self.head1[0][C:].copy_(q0.weight.reshape(C, C))
         self.head1[1][:C].copy_(p0.bias); self.head1[1][C:].copy_(q0.bias)
-        self.head2[0][0, :C].copy_(p2.weight.reshape(-1)); self.head2[0][1, C:].copy_(q2.weight.reshape(-1))
+        self.head2[0][:C].copy_(p2.weight.reshape(-1)); self.head2[0][C:].copy_(q2.weight.reshape(-1))
         self.head2[1][0:1].copy_(p2.bias); self.head2[1][1:2].copy_(q2.bias)
         for dst, i in zip(self.value, (2, 4, 6)):
             dst[0].copy_(m.value_head[i].weight)
@@ -121,20 +142,32 @@ class FusedRolloutForward:
         cid = self.calls << 8
         x = obs.to(dtype=torch.float16, memory_format=torch.channels_last)
         a16, a32 = gn_act(F.conv2d(x, self.stem[0], None, padding=1), m.stem[1], conv_bias=self.stem[1], want32=True)
+        last = len(self.blocks) - 1
+        pooled = None
         for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
             t16, _ = gn_act(F.conv2d(a16, w1, None, padding=1), blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
                             call_id=cid + k, epoch=self.epoch)
-            a16, a32 = gn_act(F.conv2d(t16, w2, None, padding=1), blk.norm2, conv_bias=b2, res32=a32, want32=True)
+            if k == last:
+                # nothing reads the fp32 residual stream after the last block except the value head's
+                # AdaptiveAvgPool2d(1): the kernel emits that mean instead of writing y32
+                pooled = torch.empty((a16.shape[0], a16.shape[1]), dtype=torch.float32, device=a16.device)
+            a16, a32 = gn_act(F.conv2d(t16, w2, None, padding=1), blk.norm2, conv_bias=b2, res32=a32,
+                              want32=k != last, pool32=pooled)
         n, c, h, w = a16.shape
         rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
-        hid = F.relu_(F.linear(rows, *self.head1))                   # [n*h*w, 2C]
-        out = F.linear(hid, *self.head2)                             # [n*h*w, 2]: policy logit, mine logit
-        logits = out[:, 0].reshape(n, h * w)
-        pooled = a32.mean(dim=(2, 3))                                # AdaptiveAvgPool2d(1) in fp32
+        if pooled is None:                                           # no residual blocks
+            pooled = a32.mean(dim=(2, 3))                            # AdaptiveAvgPool2d(1) in fp32
+        if c in (32, 64, 96, 128):
+            pol, mine = cell_heads(rows, self.head1[0], self.head1[1], self.head2[0], self.head2[1])
+        else:                                                        # other widths: the same math as library GEMMs
+            hid = F.relu_(F.linear(rows, *self.head1))               # [n*h*w, 2C]
+            pol = F.linear(hid[:, :c], self.head2[0][None, :c], self.head2[1][0:1]).squeeze(-1)
+            mine = F.linear(hid[:, c:], self.head2[0][None, c:], self.head2[1][1:2]).squeeze(-1)
+        logits = pol.reshape(n, h * w)
         v = F.relu_(F.linear(pooled.to(torch.float16), *self.value[0]))
         v = F.relu_(F.linear(v, *self.value[1]))
         value = F.linear(v, *self.value[2]).squeeze(-1)
         if not return_mine:
             return logits, value
-        return logits, value, out[:, 1].reshape(n, 1, h, w)
+        return logits, value, mine.reshape(n, 1, h, w)

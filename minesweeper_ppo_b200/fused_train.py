@@ -43,7 +43,7 @@ class GnAct(torch.autograd.Function):
                               gamma.data_ptr(), beta.data_ptr(), y16.data_ptr(), None if y32 is None else y32.data_ptr(),
                               N, H * W, C, groups, float(eps), int(relu), float(drop_p), int(seed) & (2**64 - 1),
                               int(call_id) & (2**64 - 1), None, mean.data_ptr(), rstd.data_ptr(), mask.data_ptr(),
-                              torch.cuda.current_stream(dev).cuda_stream)
+                              None, torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "msw_gn_act")
         ctx.save_for_backward(x16, cb, gamma, mean, rstd, mask)
         ctx.meta = (groups, float(drop_p), res32 is not None)

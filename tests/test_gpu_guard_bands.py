@@ -87,11 +87,14 @@ def test_sampler_and_gn_outputs_stay_inside_their_windows(A, n):
     x = torch.randn(n, C, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last)
     ry16, y16, ny16 = _window(torch, (n, H, W, C), torch.float16)
     ry32, y32, ny32 = _window(torch, (n, H, W, C), torch.float32)
+    rpl, pool, npl = _window(torch, (n, C), torch.float32)
     gn = torch.nn.GroupNorm(G, C).cuda()
     rc = L.msw_gn_act(x.data_ptr(), None, None, gn.weight.data_ptr(), gn.bias.data_ptr(), y16.data_ptr(), y32.data_ptr(),
-                      n, H * W, C, G, 1e-5, 1, 0.0, 0, 0, None, None, None, None, torch.cuda.current_stream().cuda_stream)
+                      n, H * W, C, G, 1e-5, 1, 0.0, 0, 0, None, None, None, None, pool.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
-    assert _intact(ry16, ny16) and _intact(ry32, ny32)
+    assert _intact(ry16, ny16) and _intact(ry32, ny32) and _intact(rpl, npl)
     want = torch.relu(gn(x.float())).permute(0, 2, 3, 1)
     assert float((y32 - want.detach()).abs().max()) < 1e-4
+    assert float((pool - want.detach().mean(dim=(1, 2))).abs().max()) < 1e-5

@@ -152,6 +152,47 @@ def test_fused_forward_matches_autocast_module(C, blocks, HW):
     assert float((ratio - 1 / 0.75).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("C,R", [(64, 1000), (96, 128 * 700 + 5), (32, 77), (128, 4096)])
+def test_cell_heads_match_torch(C, R):
+    """msw_cell_heads vs the same two-layer heads as fp16 torch linears (fp32 accumulation, hidden layer
+    rounded to fp16 before the ReLU), including a ragged last tile and more tiles than resident CTAs."""
+    import torch
+    from minesweeper_ppo_b200.fused_forward import cell_heads
+    g = torch.Generator(device="cuda").manual_seed(C + R)
+    rows = torch.randn((R, C), device="cuda", generator=g).half()
+    w1 = (torch.randn((2 * C, C), device="cuda", generator=g) / C ** 0.5).half()
+    b1 = (0.1 * torch.randn((2 * C,), device="cuda", generator=g)).half()
+    w2 = (torch.randn((2 * C,), device="cuda", generator=g) / C ** 0.5).half()
+    b2 = torch.tensor([0.25, -0.5], device="cuda").half()
+    pol, mine = cell_heads(rows, w1, b1, w2, b2)
+    pol2, mine2 = cell_heads(rows, w1, b1, w2, b2)
+    assert torch.equal(pol, pol2) and torch.equal(mine, mine2)
+    hid = torch.relu((rows.float() @ w1.float().t() + b1.float()).half()).float()
+    want_p = (hid[:, :C] @ w2[:C].float() + b2[0].float()).half()
+    want_m = (hid[:, C:] @ w2[C:].float() + b2[1].float()).half()
+    for got, want in ((pol, want_p), (mine, want_m)):
+        assert got.shape == (R,) and got.dtype == torch.float16
+        # one fp16 ulp of the output scale (summation order differs) plus hidden units that round across an ulp
+        assert float((got.float() - want.float()).abs().max()) <= 4e-3 * (float(want.float().abs().max()) + 1.0)
+
+
+def test_gn_act_pooled_output():
+    """msw_gn_act pool32 = spatial mean of the fp32 output, with and without writing y32."""
+    import torch
+    from minesweeper_ppo_b200.fused_forward import gn_act
+    torch.manual_seed(5)
+    for C, H, W in ((96, 16, 16), (32, 3, 5)):
+        gn = torch.nn.GroupNorm(C // 16, C).cuda()
+        z = torch.randn(9, C, H, W, device="cuda").half().contiguous(memory_format=torch.channels_last)
+        r = torch.randn(9, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+        pool_a = torch.empty((9, C), device="cuda")
+        pool_b = torch.empty((9, C), device="cuda")
+        y16a, y32 = gn_act(z, gn, res32=r, want32=True, pool32=pool_a)
+        y16b, none = gn_act(z, gn, res32=r, want32=False, pool32=pool_b)
+        assert none is None and torch.equal(y16a, y16b) and torch.equal(pool_a, pool_b)
+        assert float((pool_a - y32.mean(dim=(2, 3))).abs().max()) <= 1e-5 * (float(y32.abs().max()) + 1)
+
+
 def test_eval_compat_c1():
     """BASELINE.json configs[0]: eval yaml env (16x16x40), 64 envs, 256 episodes, random-init medium
     policy, greedy argmax through the NumPy API and the vec.envs[i] views.  An untrained greedy
