@@ -172,6 +172,23 @@ int msw_gather_encode(const msw_env_desc *desc, const uint32_t *snap_mines,
 int msw_forced_subset(const msw_env_desc *desc, const msw_state *st, int64_t n,
                       uint32_t *out_bits, void *stream);
 
+/* avoidability.analyze_avoidability (avoidability.py:145-394; SURVEY section 8
+ * row f4) for every env at once: frontier components, unit + subset rules and,
+ * when those find no safe cell, the exact per-component feasibility search.
+ * safe_bits [n][wpb]: bitboard of forced_safe_cells; comp_of_cell [n][H*W]:
+ * smallest cell index of the frontier component a cell belongs to (-1 off the
+ * frontier); comp_size [n][H*W]: size of the component whose smallest cell is
+ * that index (0 elsewhere) -- the non-zero entries in index order are the
+ * reference's component_sizes list; flags [n]: bit 0 avoidable, bit 1 frontier
+ * non-empty, bit 2 first_click_done, bit 3 the exact search ran out of its
+ * per-lane step budget (search_budget, 0 = default 2^23; the cells it could
+ * not decide are reported as not safe).  The chosen-cell fields of the
+ * reference's result follow from these arrays: chosen_is_forced_safe =
+ * safe[chosen], chosen_component_size = comp_size[comp_of_cell[chosen]]. */
+int msw_avoidability(const msw_env_desc *desc, const msw_state *st, int64_t n,
+                     uint32_t *safe_bits, int16_t *comp_of_cell, int16_t *comp_size,
+                     uint8_t *flags, uint32_t search_budget, void *stream);
+
 /* Synthetic action source for benchmarks/tests: a
  * uniformly random unrevealed cell per env (valid_only=1; 0 if none) or a
  * uniformly random cell (valid_only=0).  Writes whichever of a32/a64 is

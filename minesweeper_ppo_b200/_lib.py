@@ -74,6 +74,8 @@ SIGNATURES = {
     "msw_gather_encode": (C.c_int, [_P(EnvDesc)] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int64,
                                     _P(EncodeOut), C.c_void_p]),
     "msw_forced_subset": (C.c_int, [_P(EnvDesc), _P(State), C.c_int64, C.c_void_p, C.c_void_p]),
+    "msw_avoidability": (C.c_int, [_P(EnvDesc), _P(State), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_uint32, C.c_void_p]),
 }
 
 _lib = None

@@ -349,6 +349,26 @@ class VecMinesweeper:
             u["subset"] = np.unpackbits(raw, axis=1, count=self.HW, bitorder="little").astype(bool)
         return u["subset"]
 
+    def avoidability(self, search_budget: int = 0) -> Dict[str, np.ndarray]:
+        """avoidability.analyze_avoidability (avoidability.py:145-394) for every env in one launch, in the
+        array form of msw_avoidability: {"safe": bool [n,HW], "comp_of_cell": i16 [n,HW], "comp_size": i16
+        [n,HW], "flags": u8 [n]} (cached until the next step / reset)."""
+        u = self._unpacked()
+        if "avoid" not in u:
+            n, HW, dev = self.num_envs, self.HW, self.device
+            bits = torch.empty((n, self.wpb), dtype=torch.int32, device=dev)
+            coc = torch.empty((n, HW), dtype=torch.int16, device=dev)
+            cs = torch.empty((n, HW), dtype=torch.int16, device=dev)
+            fl = torch.empty((n,), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(self._L.msw_avoidability(C.byref(self._desc), C.byref(self._state), n, bits.data_ptr(),
+                                                    coc.data_ptr(), cs.data_ptr(), fl.data_ptr(),
+                                                    int(search_budget) & 0xFFFFFFFF, self._stream()), "msw_avoidability")
+            raw = bits.cpu().numpy().view(np.uint8).reshape(n, -1)
+            u["avoid"] = {"safe": np.unpackbits(raw, axis=1, count=HW, bitorder="little").astype(bool),
+                          "comp_of_cell": coc.cpu().numpy(), "comp_size": cs.cpu().numpy(), "flags": fl.cpu().numpy()}
+        return u["avoid"]
+
     def random_actions(self, step_index: int, valid_only: bool = True, seed: int = 1,
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Synthetic action source: uniformly random unrevealed cell

@@ -123,6 +123,16 @@ void orc_late_start(const orc_cfg *cfg, int64_t n, int64_t env_id_base, orc_stat
  * "subset_reveal" of env i.  Restated with the reference's all-pairs loop. */
 void orc_forced_subset(const orc_cfg *cfg, int64_t n, const orc_state *st, uint8_t *out);
 
+/* avoidability.analyze_avoidability (avoidability.py:145-394) for every env (msw_oracle_avoid.c).
+ * safe[i][cell] = 1 for forced_safe_cells; comp_of_cell[i][cell] = smallest cell index of the frontier
+ * component the cell belongs to (-1 off the frontier); comp_size[i][cell] = size of the component whose
+ * smallest cell is `cell` (0 elsewhere), so the non-zero entries in index order are component_sizes;
+ * flags[i]: bit 0 avoidable, bit 1 frontier non-empty, bit 2 first_click_done.  The chosen-cell fields
+ * of the result follow from these (chosen_is_forced_safe = safe[chosen] on the frontier,
+ * chosen_component_size = comp_size[comp_of_cell[chosen]]). */
+void orc_avoidability(const orc_cfg *cfg, int64_t n, const orc_state *st, uint8_t *safe,
+                      int16_t *comp_of_cell, int16_t *comp_size, uint8_t *flags);
+
 /* buffers.py:78-94 in IEEE fp32 without contraction. */
 void orc_gae(int64_t T, int64_t N, const float *rewards, const float *values,
              const uint8_t *dones, const float *last_values, float gamma_f32,

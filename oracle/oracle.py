@@ -27,7 +27,7 @@ OBS_CHANNELS = 10  # env.py:79-85
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed recipe (oracle/Makefile)."""
-    src = [os.path.join(_HERE, f) for f in ("msw_oracle.c", "msw_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("msw_oracle.c", "msw_oracle_avoid.c", "msw_oracle.h", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src
     )
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         L.orc_late_start.argtypes = [C.POINTER(_Cfg), C.c_int64, C.c_int64, C.POINTER(_State), C.c_void_p, C.c_uint64,
                                      C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_forced_subset.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State), C.c_void_p]
+        L.orc_avoidability.argtypes = [C.POINTER(_Cfg), C.c_int64, C.POINTER(_State)] + [C.c_void_p] * 4
         L.orc_gae.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 2
         _lib = L
     return _lib
@@ -235,6 +236,17 @@ class OracleVecEnv:
         out = np.zeros((self.num_envs, self.HW), np.uint8)
         lib().orc_forced_subset(C.byref(self._ccfg), self.num_envs, C.byref(self._st), out.ctypes.data)
         return out.astype(bool)
+
+    def avoidability(self) -> Dict[str, np.ndarray]:
+        """avoidability.analyze_avoidability for every env, in the array form documented in msw_oracle.h:
+        {"safe": bool [n,HW], "comp_of_cell": i16 [n,HW], "comp_size": i16 [n,HW], "flags": u8 [n]}."""
+        n, HW = self.num_envs, self.HW
+        safe = np.zeros((n, HW), np.uint8)
+        coc, cs = np.zeros((n, HW), np.int16), np.zeros((n, HW), np.int16)
+        flags = np.zeros((n,), np.uint8)
+        lib().orc_avoidability(C.byref(self._ccfg), n, C.byref(self._st), safe.ctypes.data, coc.ctypes.data,
+                               cs.ctypes.data, flags.ctypes.data)
+        return {"safe": safe.astype(bool), "comp_of_cell": coc, "comp_size": cs, "flags": flags}
 
     def _late(self, sel, obs, mask, lab, val):
         """env.py:406-414: late start on the envs just reset, then observe them again."""

@@ -384,7 +384,128 @@ def run_forced_subset_case():
     np.savez_compressed(os.path.join(OUT, "forced_subset.npz"), **out)
 
 
+def run_avoidability_case():
+    """avoidability.analyze_avoidability (avoidability.py:145-394) on mid-game states (late start +
+    random valid play), with the chosen cell eval.py:352 would pass: the action about to be played.
+    States where the reference's search needs more than a few seconds are skipped (and counted)."""
+    import time
+    from minesweeper.avoidability import analyze_avoidability
+    out = {"names": []}
+    cases = {
+        "16x16x40": (EnvConfig(H=16, W=16, mine_count=40, step_penalty=1e-4), dict(prob=0.8, min_hidden=20, max_hidden=150), 40, 6),
+        "8x8x10": (EnvConfig(), dict(prob=0.8, min_hidden=4, max_hidden=40), 64, 6),
+        "16x30x99": (EnvConfig(H=16, W=30, mine_count=99), dict(prob=0.8, min_hidden=40, max_hidden=300), 16, 5),
+        "5x7x6": (EnvConfig(H=5, W=7, mine_count=6), dict(prob=0.5, min_hidden=3, max_hidden=20), 64, 6),
+        "9x9x30_dense": (EnvConfig(H=9, W=9, mine_count=30), dict(prob=0.7, min_hidden=5, max_hidden=40), 48, 6),
+        "16x16x90_dense": (EnvConfig(H=16, W=16, mine_count=90), dict(prob=0.9, min_hidden=10, max_hidden=120), 48, 5),
+        "6x6x14_dense": (EnvConfig(H=6, W=6, mine_count=14), dict(prob=0.9, min_hidden=2, max_hidden=16), 64, 6),
+    }
+    from minesweeper import avoidability as ref_av
+    searches = [0]
+    orig_feasible = ref_av._ConstraintSolver.is_feasible
+
+    def counting_feasible(self, forced=None):
+        searches[0] += 1
+        return orig_feasible(self, forced)
+
+    ref_av._ConstraintSolver.is_feasible = counting_feasible      # wrapped, not edited: counts exact searches
+    for name, (cfg, ls, N, steps) in cases.items():
+        HW = cfg.H * cfg.W
+        vec = VecMinesweeper(N, cfg, seed=31, late_start_cfg=ls, late_start_seed=32)
+        b = vec.reset()
+        rng = np.random.default_rng(3)
+        rows = {k: [] for k in ("rev", "mine", "fcd", "chosen", "avoidable", "safe", "ncomp", "sizes", "cfs", "ccs")}
+        slow = 0
+        searched_states = search_found = 0
+        for t in range(steps):
+            mask = b["action_mask"]
+            s_ = rng.random(mask.shape); s_[~mask] = -1
+            actions = s_.argmax(1).astype(np.int32)
+            for i, e in enumerate(vec.envs):
+                # every third query asks about an arbitrary cell (also revealed / non-frontier ones), one in
+                # seven passes chosen_cell=None
+                q = (i + t) % 21
+                chosen = None if q % 7 == 6 else (int(rng.integers(0, HW)) if q % 3 == 2 else int(actions[i]))
+                t0 = time.perf_counter()
+                before = searches[0]
+                res = analyze_avoidability(e, chosen)
+                slow += time.perf_counter() - t0 > 5.0
+                if searches[0] > before:            # the unit/subset rules found nothing: exact search ran
+                    searched_states += 1
+                    search_found += bool(res.forced_safe_cells)
+                safe = np.zeros(HW, bool); safe[list(res.forced_safe_cells)] = True
+                sizes = np.zeros(HW, np.int16); sizes[: len(res.component_sizes)] = res.component_sizes
+                rows["rev"].append(e.revealed.reshape(-1).copy()); rows["mine"].append(e.mine_mask.reshape(-1).copy())
+                rows["fcd"].append(bool(e.first_click_done)); rows["chosen"].append(-1 if chosen is None else chosen)
+                rows["avoidable"].append(bool(res.avoidable)); rows["safe"].append(safe)
+                rows["ncomp"].append(len(res.component_sizes)); rows["sizes"].append(sizes)
+                rows["cfs"].append(bool(res.chosen_is_forced_safe))
+                rows["ccs"].append(-1 if res.chosen_component_size is None else int(res.chosen_component_size))
+            b, _, _, _ = vec.step(actions)
+        out["names"].append(name)
+        out[f"{name}_cfg"] = np.array([cfg.H, cfg.W, cfg.mine_count])
+        for key in ("rev", "mine", "safe"):
+            out[f"{name}_{key}"] = np.packbits(np.stack(rows[key]).astype(np.uint8), axis=1, bitorder="little")
+        for key, dt in (("fcd", np.uint8), ("chosen", np.int32), ("avoidable", np.uint8), ("ncomp", np.int32),
+                        ("sizes", np.int16), ("cfs", np.uint8), ("ccs", np.int32)):
+            out[f"{name}_{key}"] = np.asarray(rows[key]).astype(dt)
+        nq = len(rows["fcd"])
+        print(f"avoidability {name}: {nq} states, avoidable {int(np.sum(rows['avoidable']))}, "
+              f"forced-safe cells {int(np.stack(rows['safe']).sum())}, components {int(np.sum(rows['ncomp']))}, "
+              f"largest {int(np.stack(rows['sizes']).max())}, states that reached the exact search: {searched_states} "
+              f"(it found safe cells in {search_found}), searches > 5 s: {slow}")
+    ref_av._ConstraintSolver.is_feasible = orig_feasible
+    out["names"] = np.array(out["names"])
+    np.savez_compressed(os.path.join(OUT, "avoidability.npz"), **out)
+
+
+def run_eval_case():
+    """BASELINE configs[0] (C1) as a fixture: the UNMODIFIED reference eval.evaluate_vec (eval.py:265-511)
+    driven by tests/parity.scripted_policy (exact integer outputs on any device) on the reference env;
+    records its metric dict and, per env, every mine layout in the order it was drawn."""
+    import json
+    sys.path.insert(0, os.path.dirname(OUT))
+    import parity
+    import eval as ref_eval
+    out = {}
+    cases = {
+        "8x8x10": (EnvConfig(), 24, 96),
+        "16x16x40": (EnvConfig(H=16, W=16, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4), 16, 40),
+    }
+    for name, (cfg, num_envs, episodes) in cases.items():
+        model = parity.scripted_policy(cfg.H, cfg.W, seed=5)
+        with LayoutRecorder() as rec:
+            created = []
+            orig_init = MinesweeperEnv.__init__
+
+            def tracking_init(self, *a, **k):
+                orig_init(self, *a, **k)
+                created.append(self)
+
+            MinesweeperEnv.__init__ = tracking_init          # wrapped, not edited: env identity -> index
+            try:
+                metrics = ref_eval.evaluate_vec(model, cfg, episodes=episodes, seed=7, num_envs=num_envs)
+            finally:
+                MinesweeperEnv.__init__ = orig_init
+        index = {id(e): i for i, e in enumerate(created)}
+        env_i = np.array([index[id(e)] for e, _ in rec.log], np.int32)
+        layouts = pack(np.stack([m.reshape(-1) for _, m in rec.log]))
+        out[f"{name}_cfg"] = np.array([cfg.H, cfg.W, cfg.mine_count, num_envs, episodes, 7, 5])
+        out[f"{name}_layout_env"] = env_i
+        out[f"{name}_layout_bits"] = layouts
+        out[f"{name}_metrics"] = np.array(json.dumps(metrics))
+        print(f"eval {name}: {len(env_i)} layouts;", {k: round(v, 4) for k, v in metrics.items()})
+    out["names"] = np.array(list(cases))
+    np.savez_compressed(os.path.join(OUT, "c1_eval.npz"), **out)
+
+
 def main():
+    if "--eval-only" in sys.argv:
+        run_eval_case()
+        return
+    if "--avoid-only" in sys.argv:
+        run_avoidability_case()
+        return
     if "--subset-only" in sys.argv:
         run_forced_subset_case()
         return
@@ -409,6 +530,8 @@ def main():
     run_rollout_case()
     run_late_start_stats()
     run_forced_subset_case()
+    run_avoidability_case()
+    run_eval_case()
 
 
 if __name__ == "__main__":

@@ -146,3 +146,41 @@ class CudaAdapter:
         u = self.v._unpacked()
         return dict(revealed=u["revealed"].astype(bool), mine=u["mine"].astype(bool), counts=u["counts"].copy(),
                     first=u["meta"][:, 0].astype(bool), step_count=u["meta"][:, 1].copy())
+
+
+def scripted_policy(H: int, W: int, seed: int = 0):
+    """A deterministic stand-in for the policy network whose outputs are EXACT small integers /
+    quarter-integers in fp32 on any device (shifted adds only, no convolution kernels), so a greedy
+    evaluation gives the same trajectories on the reference (CPU) and on the CUDA env.  It prefers
+    frontier cells with small neighbouring numbers, so games run long enough to exercise the analytics."""
+    import torch
+
+    class ScriptedPolicy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.table = torch.nn.Parameter(torch.randperm(H * W, generator=g).float(), requires_grad=False)
+
+        @staticmethod
+        def _sum3x3(x):                      # [B,1,H,W] -> sum over the 3x3 neighbourhood, zero padded
+            p = torch.nn.functional.pad(x, (1, 1, 1, 1))
+            out = torch.zeros_like(x)
+            for dr in range(3):
+                for dc in range(3):
+                    out = out + p[:, :, dr:dr + H, dc:dc + W]
+            return out
+
+        def forward(self, obs, return_mine: bool = False):
+            B = obs.shape[0]
+            rev = obs[:, 0:1]
+            num = torch.zeros_like(rev)
+            for k in range(1, 9):
+                num = num + float(k) * obs[:, 1 + k:2 + k]
+            nb, ns = self._sum3x3(rev), self._sum3x3(num)
+            logits = (1024.0 * (nb > 0).float() - 16.0 * ns).reshape(B, H * W) + self.table
+            value = torch.zeros((B,), dtype=obs.dtype, device=obs.device)
+            if not return_mine:
+                return logits, value
+            return logits, value, (ns - 2.0 * nb) * 0.25
+
+    return ScriptedPolicy()

@@ -193,6 +193,54 @@ def test_gn_act_pooled_output():
         assert float((pool_a - y32.mean(dim=(2, 3))).abs().max()) <= 1e-5 * (float(y32.abs().max()) + 1)
 
 
+@pytest.mark.parametrize("name", ["8x8x10", "16x16x40"])
+def test_eval_matches_reference_metrics(name):
+    """BASELINE configs[0] (C1) end to end: tests/golden/c1_eval.npz holds the metric dict the UNMODIFIED
+    reference eval.evaluate_vec produced with parity.scripted_policy (exact integer outputs on any device)
+    and every mine layout its envs drew.  evaluate_vec of this package, on the CUDA env fed the same
+    layouts, must return the same dict: all counts-derived metrics exactly, the two belief metrics to 1e-6
+    (sigmoid differs in the last ulp between CPU and GPU)."""
+    import json
+    import math
+    from collections import deque
+    import torch
+    import minesweeper_ppo_b200 as m
+    from minesweeper_ppo_b200.evaluate import evaluate_vec
+    import parity as P
+    g = P.load("c1_eval")
+    H, W, M, num_envs, episodes, seed, pol_seed = (int(x) for x in g[f"{name}_cfg"])
+    want = json.loads(str(g[f"{name}_metrics"]))
+    layouts = P.unpack(g[f"{name}_layout_bits"], H * W)
+    queues = [deque() for _ in range(num_envs)]
+    for i, bits in zip(g[f"{name}_layout_env"], layouts):
+        queues[int(i)].append(bits)
+
+    class ReplayVec(m.VecMinesweeper):
+        """The env under test, drawing the reference's layouts: every env about to make its first click
+        of an episode takes the next layout the reference drew for that env."""
+
+        def step(self, actions):
+            fresh = self._meta[:, 0].cpu().numpy() == 0
+            mine = np.zeros((self.num_envs, self.HW), bool)
+            for i in np.flatnonzero(fresh):
+                mine[i] = queues[i].popleft()
+            self.inject_layouts(mine, fresh)
+            return super().step(actions)
+
+    cfg = m.EnvConfig(H=H, W=W, mine_count=M, step_penalty=1e-4)
+    model = P.scripted_policy(H, W, seed=pol_seed).cuda()
+    got = evaluate_vec(model, cfg, episodes=episodes, seed=seed, num_envs=num_envs, vec_factory=ReplayVec)
+    assert all(len(q) == 0 for q in queues), "the replay must consume exactly the layouts the reference drew"
+    for k, w in want.items():
+        v = got[k]
+        if isinstance(w, float) and math.isnan(w):
+            assert math.isnan(v), (k, v)
+        elif k.startswith("belief_"):
+            assert abs(v - w) <= 1e-6, (k, v, w)
+        else:
+            assert v == w, (k, v, w)
+
+
 def test_eval_compat_c1():
     """BASELINE.json configs[0]: eval yaml env (16x16x40), 64 envs, 256 episodes, random-init medium
     policy, greedy argmax through the NumPy API and the vec.envs[i] views.  An untrained greedy
