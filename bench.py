@@ -378,15 +378,32 @@ def bench_gae(torch, m, dev):
         torch.cuda.synchronize()
         if i >= 3:
             cold.append(a.elapsed_time(b))
-    reps = 50
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flush.zero_()
-    a.record()
-    for _ in range(reps):
-        buf.compute_gae(last, 0.995, 0.95)
-    b.record()
-    torch.cuda.synchronize()
-    warm_ms = a.elapsed_time(b) / reps
+    def graph_us(b_, last_, reps=20):
+        """Device time per launch with the host out of the way: `reps` launches captured in one CUDA graph."""
+        gr, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            b_.compute_gae(last_, 0.995, 0.95)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gr, stream=st):
+                for _ in range(reps):
+                    b_.compute_gae(last_, 0.995, 0.95)
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gr.replay(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    warm_ms = graph_us(buf, last) / 1e3
+    # the same kernel where it is bandwidth- rather than latency-bound: 64x the columns (1.14 GB of traffic >> L2)
+    NL = 64 * N
+    big = m.RolloutBuffer(NL, T, (1, 1, 1), 1, dev)
+    big.dones.copy_(torch.rand((T * NL,), device=dev, generator=g) < 0.15)
+    big.rewards.copy_(torch.where(big.dones, consts[1], consts[0]))
+    big.values.copy_(0.5 * torch.randn((T * NL,), device=dev, generator=g))
+    big_us = graph_us(big, 0.5 * torch.randn((NL,), device=dev, generator=g), reps=5)
+    big_bytes = 17 * T * NL + 4 * NL
+    del big
     ms = float(np.median(cold))
     nbytes = 17 * T * N + 4 * N
     peak, _ = measured_peak_gbs()
@@ -411,8 +428,13 @@ def bench_gae(torch, m, dev):
             "bit_identical_to_cpu_loop": same, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
             "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "l2": "1 GB flush write before every timed launch (cold)",
             "back_to_back_us": warm_ms * 1e3,
-            "note": "cold = inputs in HBM; back_to_back = 50 launches in a row (17.9 MB working set stays in L2, "
-                    "as it does right after a rollout); latency-bound: 8,192 independent chains of 128 dependent steps"}
+            "large": {"T": T, "N": NL, "kernel_us": big_us, "algorithmic_bytes": big_bytes,
+                      "achieved_gbs": big_bytes / big_us / 1e3, "frac_of_hbm_peak": big_bytes / big_us / 1e3 / peak},
+            "note": "cold = inputs in HBM, CUDA events around one launch (about 3 us of that is event/launch gap: ncu "
+                    "shows 11 us); back_to_back = 20 launches replayed from one CUDA graph (17.9 MB working set stays "
+                    "in L2, as it does right after a rollout); at C3 size the kernel is latency-bound (8,192 chains "
+                    "of 128 dependent steps, one 36 KB tile per CTA); `large` is the same kernel at 64x the columns, "
+                    "where it is HBM-bound"}
 
 
 def bench_rollout(torch, m, dev, rank, world, reduce_max):

@@ -23,6 +23,7 @@
 #include "../../include/msw_b200.h"
 #include "msw_error.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -138,6 +139,162 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
     }
 }
 
+// ---------------------------------------------------------------------------
+// TMA variant (the default when N % 16 == 0 and the arrays are 16-byte aligned).  Measured on one B200
+// (profiles/r01g_gae.md): the same 7.1 us as the plain-load kernel at C3 size (T=128, N=8,192: both are
+// latency-bound, one tile per CTA), but 5.1 TB/s instead of 2.6 TB/s at N=524,288, where the kernel is
+// HBM-bound.
+//
+// The tile loads and stores above cost 48 LDG + 48 STS + 32 STG per thread plus their address
+// arithmetic, and the memory system sees them as ~100 k separate 128-byte requests.  Here one
+// thread moves each [128 x 32] tile with a single cp.async.bulk.tensor.2d (rewards, values, dones
+// in; advantages, returns out), completion on an mbarrier, so the CTA's whole 36 KB is in flight
+// from the first cycle and no thread spends instructions on the copies.  Out-of-range rows and
+// columns are zero-filled on load and clipped on store by the tensor map, so ragged T and N need
+// no predicates.  Arithmetic and its order are exactly those of gae_kernel above.
+// ---------------------------------------------------------------------------
+constexpr int TG_ROWS = 128, TG_COLS = 32, TG_THREADS = 128;
+
+struct TmaGaeSmem {
+    alignas(128) float r[TG_ROWS][TG_COLS];      // rewards in, delta, advantages out
+    alignas(128) float v[TG_ROWS][TG_COLS];      // values in, returns out
+    alignas(128) float c[TG_ROWS][TG_COLS];      // (gamma*lam) * nnt
+    alignas(128) uint8_t d[TG_ROWS][TG_COLS];
+    float gvn[TG_COLS];                          // gamma * value of the row after this tile's last one
+    alignas(8) unsigned long long bar;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+
+__global__ void __launch_bounds__(TG_THREADS)
+gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_constant__ CUtensorMap m_values,
+               const __grid_constant__ CUtensorMap m_dones, const __grid_constant__ CUtensorMap m_adv,
+               const __grid_constant__ CUtensorMap m_ret, const float *__restrict__ last_values, long long T,
+               long long N, float gamma, float gamma_lam, int prescaled)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TmaGaeSmem &S = *reinterpret_cast<TmaGaeSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * TG_COLS;
+    const bool chain = warp == 0;
+    constexpr unsigned TILE_BYTES = TG_ROWS * TG_COLS * (4 + 4 + 1);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&S.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float last = 0.0f;                                          // buffers.py:86
+    if (chain) {                                                // buffers.py:88 (t == T-1)
+        const float lv = col0 + lane < N ? last_values[col0 + lane] : 0.0f;
+        S.gvn[lane] = prescaled ? lv : __fmul_rn(gamma, lv);    // prescaled: already gamma*last_value (fp16 bootstrap)
+    }
+    __syncthreads();
+
+    const long long tiles = (T + TG_ROWS - 1) / TG_ROWS;
+    unsigned parity = 0;
+    for (long long k = tiles - 1; k >= 0; --k, parity ^= 1u) {
+        const int row0 = (int)(k * TG_ROWS);
+        const int rows = (int)(T - row0 < TG_ROWS ? T - row0 : TG_ROWS);
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&S.bar)), "r"(TILE_BYTES) : "memory");
+            tma_load_2d(&S.r[0][0], &m_rewards, col0, row0, &S.bar);
+            tma_load_2d(&S.v[0][0], &m_values, col0, row0, &S.bar);
+            tma_load_2d(&S.d[0][0], &m_dones, col0, row0, &S.bar);
+        }
+        {
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_u32(&S.bar)), "r"(parity) : "memory");
+        }
+        // ---- delta[t] = (r[t] + (gamma * v[t+1]) * nnt[t]) - v[t] (buffers.py:88-90) and c[t] =
+        // (gamma*lam) * nnt[t]: warp w owns rows w, w+4, ..., lane = column
+#pragma unroll 8
+        for (int i = warp; i < rows; i += TG_THREADS / 32) {
+            const float gv = i + 1 < rows ? __fmul_rn(gamma, S.v[i + 1][lane]) : S.gvn[lane];
+            const bool dn = S.d[i][lane] != 0;
+            S.r[i][lane] = __fsub_rn(__fadd_rn(S.r[i][lane], __fmul_rn(gv, dn ? 0.0f : 1.0f)), S.v[i][lane]);
+            S.c[i][lane] = dn ? 0.0f : gamma_lam;               // == gamma_lam * nnt exactly
+        }
+        __syncthreads();
+        // ---- chain: last = delta + c * last (buffers.py:91), 8 rows per batch read ahead of the dependent math
+        if (chain) {
+            S.gvn[lane] = __fmul_rn(gamma, S.v[0][lane]);       // for the tile before this one in time
+            for (int hi = rows; hi > 0; hi -= 8) {
+                float dl[8], gl[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = hi - 1 - q >= 0 ? hi - 1 - q : 0;
+                    dl[q] = S.r[i][lane];
+                    gl[q] = S.c[i][lane];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = hi - 1 - q;
+                    if (i >= 0) {
+                        last = __fadd_rn(dl[q], __fmul_rn(gl[q], last));
+                        S.r[i][lane] = last;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- returns = advantages + values (buffers.py:94), in place over the values
+#pragma unroll 8
+        for (int i = warp; i < rows; i += TG_THREADS / 32) S.v[i][lane] = __fadd_rn(S.r[i][lane], S.v[i][lane]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA store
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&m_adv, col0, row0, &S.r[0][0]);
+            tma_store_2d(&m_ret, col0, row0, &S.v[0][0]);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (k > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile buffers are reused
+        }
+        if (k > 0) __syncthreads();
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static const EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [T][N] row-major array of `es`-byte elements, box = [TG_ROWS][TG_COLS]
+static bool make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, size_t es, int64_t T, int64_t N)
+{
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * es};
+    const cuuint32_t box[2] = {TG_COLS, TG_ROWS}, estr[2] = {1, 1};
+    return encode_tiled_fn()(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace msw
 
 extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t *dones,
@@ -160,6 +317,32 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
     const int cols = forced == 16 ? 16 : 32;
     const long long blocks = (N + cols - 1) / cols;
     if (blocks > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: N too large");
+    // TMA path: the tensor maps need 16-byte aligned bases and row pitches (N bytes for dones).
+    // MSW_GAE_TMA=0 forces the plain-load kernel (measurements, and the path for ragged N).
+    static const bool tma_on = [] {
+        const char *e = getenv("MSW_GAE_TMA");
+        return !(e && e[0] == '0');
+    }();
+    const uintptr_t bases = (uintptr_t)rewards | (uintptr_t)values | (uintptr_t)dones | (uintptr_t)advantages | (uintptr_t)returns;
+    if (tma_on && forced == 0 && N % 16 == 0 && (bases & 15u) == 0 && T <= 0x7fffffffLL && encode_tiled_fn()) {
+        CUtensorMap mr, mv, md, ma, mt;
+        if (!make_map(&mr, rewards, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
+            !make_map(&mv, values, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
+            !make_map(&md, dones, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, T, N) ||
+            !make_map(&ma, advantages, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
+            !make_map(&mt, returns, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N))
+            return fail(MSW_ERR_ARG, "msw_gae: cuTensorMapEncodeTiled failed (T=%lld N=%lld)", (long long)T, (long long)N);
+        static thread_local bool configured = false;
+        if (!configured) {
+            MSW_CUDA_TRY(cudaFuncSetAttribute(gae_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(TmaGaeSmem)));
+            configured = true;
+        }
+        gae_tma_kernel<<<(unsigned)blocks, TG_THREADS, sizeof(TmaGaeSmem), (cudaStream_t)stream>>>(
+            mr, mv, md, ma, mt, last_values, T, N, gamma_f32, gamma_lam_f32, (int)last_values_prescaled);
+        MSW_CUDA_TRY(cudaGetLastError());
+        return MSW_OK;
+    }
 #define MSW_GAE_LAUNCH(C)                                                                           \
     gae_kernel<C><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(                  \
         rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32, \
