@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace msw {
 
@@ -60,6 +61,7 @@ struct GnParams {
     float *y32;             // nullable [n][HW][C]
     int HW, C, G, cpg, CB, PPB;
     unsigned tile_bytes;
+    int bulk;                       // 1: the fp16 sample moves with ONE cp.async.bulk each way (load, y16 store)
     float eps, inv_count, drop_p, drop_scale;
     int relu;
     uint32_t k0, k1, call_lo, call_hi;
@@ -100,10 +102,31 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
 
     const long long n = blockIdx.x;
     const int buf = 0;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned sample_bytes = (unsigned)p.HW * (unsigned)p.C * 2u;
     if (n < n_samples) {
-        stage(n, 0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint4 *tile = reinterpret_cast<const uint4 *>(smem_raw + buf * tile_bytes);
+        if (p.bulk) {
+            // the sample is one contiguous block of global memory: one bulk copy, completion on an mbarrier
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+            if (tid == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sample_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"((unsigned)__cvta_generic_to_shared(smem_raw)),
+                                "l"(reinterpret_cast<const uint4 *>(p.x) + n * (long long)p.HW * p.CB), "r"(sample_bytes), "r"(bar)
+                             : "memory");
+            }
+            __syncthreads();                          // the barrier is initialised before anyone polls it
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }"
+                             : "=r"(done) : "r"(bar) : "memory");
+        } else {
+            stage(n, 0);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        uint4 *tile = reinterpret_cast<uint4 *>(smem_raw + buf * tile_bytes);
         const long long base = n * (long long)p.HW * p.CB;                       // in uint4 chunks
 
         // ONE pass for the statistics: per thread, shifted sums S1 = sum (v - c), S2 = sum (v - c)^2 of
@@ -240,8 +263,19 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
                     __half2 *oh = reinterpret_cast<__half2 *>(&out);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
-                    y16[idx] = out;
+                    if (p.bulk) tile[idx] = out;      // in place over the thread's own input chunk
+                    else y16[idx] = out;
                 }
+            }
+        }
+        if (p.bulk && p.y16) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the bulk store
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(reinterpret_cast<uint4 *>(p.y16) + n * (long long)p.HW * p.CB),
+                                "r"((unsigned)__cvta_generic_to_shared(smem_raw)), "r"(sample_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group.read 0;" ::: "memory");
             }
         }
         if (p.pool) {
@@ -465,6 +499,12 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.epoch = epoch;
     p.pool = pool32;
     p.tile_bytes = (unsigned)tile_bytes;
+    // MSW_GN_BULK=0 selects the per-thread cp.async / STG path (measurements: profiles/r01g_gn_bulk.txt)
+    static const int bulk = [] {
+        const char *e = getenv("MSW_GN_BULK");
+        return e ? atoi(e) : 1;
+    }();
+    p.bulk = bulk;
     if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))
         return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;
