@@ -7,6 +7,7 @@ from minesweeper_ppo_b200.fused_forward import FusedRolloutForward
 from torch.profiler import profile, ProfilerActivity
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+torch.backends.cudnn.benchmark = os.environ.get("CUDNN_BENCHMARK", "0") == "1"
 model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
                       model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).cuda()
 x = (torch.rand(N, 10, 16, 16, device="cuda") < 0.3).float()
