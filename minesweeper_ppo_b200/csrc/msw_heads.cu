@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace msw {
 
@@ -178,6 +179,10 @@ static int launch_heads(const void *a16, const void *w1, const void *b1, const v
     return MSW_OK;
 }
 
+// tcgen05 / TMEM implementation of the same operation (msw_heads_tc.cu); -1 = not applicable
+int heads_tc_launch(int C, const void *a16, const void *w1, const void *b1, const void *w2, const void *b2,
+                    void *out_policy, void *out_mine, int64_t R, cudaStream_t stream);
+
 }  // namespace msw
 
 extern "C" int msw_cell_heads(const void *a16, const void *w1, const void *b1, const void *w2, const void *b2,
@@ -191,6 +196,15 @@ extern "C" int msw_cell_heads(const void *a16, const void *w1, const void *b1, c
         return fail(MSW_ERR_ALIGN, "msw_cell_heads: a16 and w1 must be 16-byte aligned");
     if (rows == 0) return MSW_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    // MSW_HEADS=mma selects the mma.sync kernel of this file also where the tcgen05 kernel applies
+    static const bool want_tc = [] {
+        const char *e = getenv("MSW_HEADS");
+        return !(e && e[0] == 'm');
+    }();
+    if (want_tc) {
+        const int rc = heads_tc_launch(C, a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
+        if (rc >= 0) return rc;
+    }
     switch (C) {
     case 32: return launch_heads<32>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
     case 64: return launch_heads<64>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
