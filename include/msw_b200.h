@@ -256,6 +256,13 @@ int msw_cell_heads(const void *a16, const void *w1, const void *b1, const void *
                    const void *b2, void *out_policy, void *out_mine, int64_t rows,
                    int32_t C, void *stream);
 
+/* 3x3 "same" convolution of the residual trunk (cnn_residual.py:10-13: Conv2d(C, C, 3, padding=1)) on the
+ * tcgen05 tensor cores, for the shape the medium config uses: 16x16 boards, C = 96.  x16: fp16 NHWC
+ * [n][16][16][C]; w_taps16: fp16 [9][C_out][C_in], tap = ky*3 + kx of the module's [C_out][C_in][3][3]
+ * weight; y16: fp16 NHWC conv output WITHOUT bias (msw_gn_act adds it), fp32 accumulation. */
+int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
+                int32_t C, void *stream);
+
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and
  * Dropout2d) come from the forward call (all three nullable there, given

@@ -69,6 +69,29 @@ def cell_heads(rows16: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: tor
     return out[0], out[1]
 
 
+def conv3x3_taps(weight: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [C_out, C_in, 3, 3] -> the fp16 [9, C_out, C_in] tap-major layout msw_conv3x3 reads."""
+    co, ci = weight.shape[0], weight.shape[1]
+    return weight.detach().permute(2, 3, 0, 1).to(torch.float16).reshape(9, co, ci).contiguous()
+
+
+def conv3x3(x16: torch.Tensor, taps16: torch.Tensor) -> torch.Tensor:
+    """msw_conv3x3: x16 fp16 [N,C,16,16] channels_last, taps16 from `conv3x3_taps` -> fp16 conv output
+    (no bias), same shape / memory format."""
+    L = _lib.load()
+    N, C, H, W = x16.shape
+    if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("conv3x3: x must be fp16 channels_last")
+    if taps16.dtype != torch.float16 or tuple(taps16.shape) != (9, C, C) or not taps16.is_contiguous():
+        raise ValueError("conv3x3: taps must be contiguous fp16 [9, C, C]")
+    y = torch.empty_like(x16, memory_format=torch.channels_last)
+    with torch.cuda.device(x16.device):
+        rc = L.msw_conv3x3(x16.data_ptr(), taps16.data_ptr(), y.data_ptr(), N, H, W, C,
+                           torch.cuda.current_stream(x16.device).cuda_stream)
+    _lib.check(rc, "msw_conv3x3")
+    return y
+
+
 class FusedRolloutForward:
     """Callable with the module's `(obs, return_mine)` signature, for use under torch.no_grad()."""
 
