@@ -151,13 +151,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const unsigned s = it % STAGES, ph = (it / STAGES) & 1u;
-            cv_bar_wait(tempty, (it & 1u) ^ 1u);          // the epilogue has drained the previous tile
             cv_bar_wait(full(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned a0 = base + OFF_A + s * A_STAGE, a1 = a0 + A0_BYTES;
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const unsigned d = tmem + dx * C;                            // accumulator of this horizontal tap
+                // Accumulators rotate through five 96-column TMEM slots: tile `it` uses slots 3*it + dx (mod 5).
+                // Its first two are free as soon as the epilogue of tile it-2 is done (guaranteed, see below),
+                // so two thirds of this tile's MMAs overlap the previous tile's epilogue; only the third slot
+                // is the one tile it-1 used first, and waits for that epilogue.
+                if (dx == 2) {
+                    cv_bar_wait(tempty, (it & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const unsigned d = tmem + ((3u * it + dx) % 5u) * C;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
                     const int tap = dy * 3 + dx;
@@ -187,9 +194,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
             for (int c0 = 0; c0 < 48; c0 += 16) {
                 uint32_t vm[16], v0[16], vp[16];
-                cv_ld16(trow + 0 * C + half * 48 + c0, vm);       // D_-1: contributes to the pixel on its right
-                cv_ld16(trow + 1 * C + half * 48 + c0, v0);
-                cv_ld16(trow + 2 * C + half * 48 + c0, vp);       // D_+1: contributes to the pixel on its left
+                cv_ld16(trow + ((3u * it + 0u) % 5u) * C + half * 48 + c0, vm);   // D_-1: contributes to the pixel on its right
+                cv_ld16(trow + ((3u * it + 1u) % 5u) * C + half * 48 + c0, v0);
+                cv_ld16(trow + ((3u * it + 2u) % 5u) * C + half * 48 + c0, vp);   // D_+1: contributes to the pixel on its left
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 uint32_t packed[8];
 #pragma unroll

@@ -10,6 +10,7 @@ The parameters are read from the live module, so training and rollouts share one
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -134,6 +135,10 @@ class FusedRolloutForward:
             dev = p0.weight.device
             self.stem = conv3(m.stem[0])
             self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
+            # tap-major fp16 copies of the trunk weights for msw_conv3x3 (tcgen05; 16x16 boards, 96 channels)
+            self.taps = ([(torch.empty((9, C, C), dtype=torch.float16, device=dev),
+                           torch.empty((9, C, C), dtype=torch.float16, device=dev)) for _ in m.residual_stack]
+                         if C == 96 and os.environ.get("MSW_CONV", "tc") != "cudnn" else None)
             # the two per-cell heads (1x1 -> ReLU -> 1x1) are row-wise linears on the NHWC activation:
             # one msw_cell_heads launch, the hidden layer never reaches HBM
             self.head1 = lin(2 * C, C, dev)
@@ -150,6 +155,10 @@ class FusedRolloutForward:
         for (d1, d2), b in zip(self.blocks, m.residual_stack):
             put3(d1, b.conv1)
             put3(d2, b.conv2)
+        if self.taps is not None:
+            for (t1, t2), b in zip(self.taps, m.residual_stack):
+                t1.copy_(b.conv1.weight.permute(2, 3, 0, 1).reshape(9, C, C))
+                t2.copy_(b.conv2.weight.permute(2, 3, 0, 1).reshape(9, C, C))
         self.head1[0][:C].copy_(p0.weight.reshape(C, C)); self.head1[0][C:].copy_(q0.weight.reshape(C, C))
         self.head1[1][:C].copy_(p0.bias); self.head1[1][C:].copy_(q0.bias)
         self.head2[0][:C].copy_(p2.weight.reshape(-1)); self.head2[0][C:].copy_(q2.weight.reshape(-1))
@@ -167,16 +176,18 @@ class FusedRolloutForward:
         a16, a32 = gn_act(F.conv2d(x, self.stem[0], None, padding=1), m.stem[1], conv_bias=self.stem[1], want32=True)
         last = len(self.blocks) - 1
         pooled = None
+        own_conv = self.taps is not None and tuple(a16.shape[2:]) == (16, 16)
         for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
-            t16, _ = gn_act(F.conv2d(a16, w1, None, padding=1), blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
+            c1 = conv3x3(a16, self.taps[k][0]) if own_conv else F.conv2d(a16, w1, None, padding=1)
+            t16, _ = gn_act(c1, blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
                             call_id=cid + k, epoch=self.epoch)
             if k == last:
                 # nothing reads the fp32 residual stream after the last block except the value head's
                 # AdaptiveAvgPool2d(1): the kernel emits that mean instead of writing y32
                 pooled = torch.empty((a16.shape[0], a16.shape[1]), dtype=torch.float32, device=a16.device)
-            a16, a32 = gn_act(F.conv2d(t16, w2, None, padding=1), blk.norm2, conv_bias=b2, res32=a32,
-                              want32=k != last, pool32=pooled)
+            c2 = conv3x3(t16, self.taps[k][1]) if own_conv else F.conv2d(t16, w2, None, padding=1)
+            a16, a32 = gn_act(c2, blk.norm2, conv_bias=b2, res32=a32, want32=k != last, pool32=pooled)
         n, c, h, w = a16.shape
         rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
         if pooled is None:                                           # no residual blocks
