@@ -14,8 +14,9 @@
 //     edge coincides with the lanes that have no neighbour.
 // All nine [96 x 96] weight taps stay resident in shared memory (162 KB, loaded once per persistent CTA);
 // the activation streams through a 2-stage ring.  K = 96 = one 64-channel block (128-byte swizzle) + one
-// 32-channel block (64-byte swizzle).  Roles: warp 0 TMA producer, warp 1 MMA issuer (54 tcgen05.mma of
-// 128 x 96 x 16 per tile), warp 2 TMEM allocation, warps 4-11 epilogue (each warpgroup half of the channels).
+// 32-channel block (64-byte swizzle).  Roles: warp 0 TMA producer, warp 1 MMA issuer (18 tcgen05.mma of
+// 128 x 192 x 16 and 18 of 128 x 96 x 16 per tile), warp 2 TMEM allocation, warps 4-15 epilogue (each warpgroup a
+// third of the channels).
 #include "../../include/msw_b200.h"
 #include "msw_error.h"
 
@@ -23,18 +24,19 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace msw {
 
 namespace cv {
 constexpr int C = 96, HW_W = 16, TILE_PX = 128, ROWS_IN = 10, PX_IN = ROWS_IN * HW_W;   // 160 staged pixels
-constexpr int THREADS = 384, STAGES = 2, TMEM_COLS = 512;
+constexpr int THREADS = 512, STAGES = 2, TMEM_COLS = 512;       // 4 control warps + 12 epilogue warps
 constexpr unsigned W0_TAP = C * 128u, W1_TAP = C * 64u;                 // bytes per tap: 64-ch block, 32-ch block
 constexpr unsigned W0_BYTES = 9 * W0_TAP, W1_BYTES = 9 * W1_TAP;
 constexpr unsigned A0_BYTES = PX_IN * 128u, A1_BYTES = PX_IN * 64u, A_STAGE = A0_BYTES + A1_BYTES;
 constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = OFF_W1 + W1_BYTES;
-constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], tfull, tempty, wfull
-constexpr unsigned OFF_TMEM = OFF_BAR + 7 * 8u;
+constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], tfull, d2_empty, wfull, d01_empty[2]
+constexpr unsigned OFF_TMEM = OFF_BAR + 9 * 8u;
 constexpr unsigned SMEM_BYTES = OFF_TMEM + 16u + 1024u;                 // + slack to align the base to 1024 B
 }  // namespace cv
 
@@ -98,7 +100,7 @@ __device__ __forceinline__ void cv_ld16(unsigned taddr, uint32_t (&v)[16])
 __global__ void __launch_bounds__(cv::THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
-                  __half *__restrict__ out, long long tiles)
+                  __half *__restrict__ out, long long tiles, int dbg)
 {
     using namespace cv;
     extern __shared__ unsigned char smem_dyn[];
@@ -107,14 +109,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const unsigned bars = base + OFF_BAR;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (2 + s); };
-    const unsigned tfull = bars + 8u * 4, tempty = bars + 8u * 5, wfull = bars + 8u * 6;
+    const unsigned tfull = bars + 8u * 4, d2_empty = bars + 8u * 5, wfull = bars + 8u * 6;
+    auto d01_empty = [&](unsigned b) { return bars + 8u * (7 + b); };
     volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(gen + OFF_TMEM);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { cv_bar_init(full(s), 1); cv_bar_init(empty(s), 1); }
         cv_bar_init(tfull, 1);
-        cv_bar_init(tempty, 8);
+        cv_bar_init(d2_empty, 12);
+        cv_bar_init(d01_empty(0), 12);
+        cv_bar_init(d01_empty(1), 12);
         cv_bar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -145,8 +150,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             cv_tma_4d(base + OFF_A + s * A_STAGE + A0_BYTES, &map_a1, 64, 0, y0 - 1, n, full(s));
         }
     } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer.  idesc: D = F32, A = B = F16, K-major, N = 96, M = 128.
-        constexpr unsigned idesc = (1u << 4) | ((unsigned)(C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
+        // ---- MMA issuer.  idesc: D = F32, A = B = F16, K-major, M = 128, N = 192 or 96.
+        // One MMA covers the taps dx = -1 and dx = 0 together (their weight blocks are adjacent in shared memory
+        // and their accumulators adjacent in TMEM, N = 192), a second one dx = +1 (N = 96): with three N = 96
+        // MMAs the A operand is read from shared memory three times and the tensor pipe waits for it (7 KB of
+        // operands per 48-cycle MMA > 128 B/clk).  TMEM: D_-1|D_0 double buffered at columns 0 / 192, D_+1 single
+        // buffered at 384 (2 x 288 columns do not fit).  The epilogue copies its D_+1 values to registers first
+        // and releases that buffer at once, so the N = 96 MMAs of the next tile wait for one TMEM load, not for
+        // the whole epilogue; the N = 192 MMAs only need the epilogue of the tile before the previous one.
+        constexpr unsigned idesc192 = (1u << 4) | ((unsigned)(2 * C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
+        constexpr unsigned idesc96 = (1u << 4) | ((unsigned)(C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
         cv_bar_wait(wfull, 0);
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
@@ -155,19 +168,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned a0 = base + OFF_A + s * A_STAGE, a1 = a0 + A0_BYTES;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                // Accumulators rotate through five 96-column TMEM slots: tile `it` uses slots 3*it + dx (mod 5).
-                // Its first two are free as soon as the epilogue of tile it-2 is done (guaranteed, see below),
-                // so two thirds of this tile's MMAs overlap the previous tile's epilogue; only the third slot
-                // is the one tile it-1 used first, and waits for that epilogue.
-                if (dx == 2) {
-                    cv_bar_wait(tempty, (it & 1u) ^ 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                const unsigned d = tmem + ((3u * it + dx) % 5u) * C;
+            for (int part = 0; part < 2; ++part) {
+                // part 0 reuses the D_-1|D_0 buffer of tile it-2, part 1 the D_+1 buffer of tile it-1
+                cv_bar_wait(part == 0 ? d01_empty(it & 1u) : d2_empty, part == 0 ? ((it >> 1) & 1u) ^ 1u : (it & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d = part == 0 ? tmem + (it & 1u) * 2u * C : tmem + 4u * C;
+                const unsigned idesc = part == 0 ? idesc192 : idesc96;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                    const int tap = dy * 3 + dx;
+                    const int tap = dy * 3 + 2 * part;                       // first weight block of this MMA
 #pragma unroll
                     for (int k = 0; k < 4; ++k)                              // channels 0..63: four 16-channel steps
                         cv_mma(d, cv_desc128(a0 + dy * HW_W * 128u) + 2u * k, cv_desc128(base + OFF_W0 + tap * W0_TAP) + 2u * k,
@@ -182,21 +191,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             cv_commit(tfull);
         }
     } else if (warp >= 4) {
-        // ---- epilogue: thread = pixel (TMEM lane q*32 + lane), warpgroup = half of the output channels
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        // ---- epilogue: thread = pixel (TMEM lane q*32 + lane), each of the three warpgroups a third of the channels
+        const int q = warp & 3, third = (warp - 4) >> 2;
         const int x = lane & 15;
         unsigned it = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             cv_bar_wait(tfull, it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
-            __half *dst = out + ((tile >> 1) * 256 + (tile & 1) * 128 + q * 32 + lane) * (long long)C + half * 48;
+            const unsigned trow = tmem + ((unsigned)(q * 32) << 16) + third * 32;
+            const unsigned d01 = trow + (it & 1u) * 2u * C, d2 = trow + 4u * C;
+            __half *dst = out + ((tile >> 1) * 256 + (tile & 1) * 128 + q * 32 + lane) * (long long)C + third * 32;
+            uint32_t vp[32];                       // D_+1 (contributes to the pixel on its left): copy out, release
+            {
+                uint32_t lo[16], hi[16];
+                cv_ld16(d2, lo);
+                cv_ld16(d2 + 16, hi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int c0 = 0; c0 < 48; c0 += 16) {
-                uint32_t vm[16], v0[16], vp[16];
-                cv_ld16(trow + ((3u * it + 0u) % 5u) * C + half * 48 + c0, vm);   // D_-1: contributes to the pixel on its right
-                cv_ld16(trow + ((3u * it + 1u) % 5u) * C + half * 48 + c0, v0);
-                cv_ld16(trow + ((3u * it + 2u) % 5u) * C + half * 48 + c0, vp);   // D_+1: contributes to the pixel on its left
+                for (int j = 0; j < 16; ++j) { vp[j] = lo[j]; vp[16 + j] = hi[j]; }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) cv_bar_arrive(d2_empty);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                if (dbg & 1) break;
+                uint32_t vm[16], v0[16];
+                cv_ld16(d01 + c0, vm);             // D_-1: contributes to the pixel on its right
+                cv_ld16(d01 + C + c0, v0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 uint32_t packed[8];
 #pragma unroll
@@ -205,18 +227,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j + e]), 1);
-                        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j + e]), 1);
+                        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[c0 + j + e]), 1);
                         r[e] = __uint_as_float(v0[j + e]) + (x > 0 ? left : 0.0f) + (x < 15 ? right : 0.0f);
                     }
                     const __half2 h = __floats2half2_rn(r[0], r[1]);
                     packed[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
                 }
-                *reinterpret_cast<uint4 *>(dst + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4 *>(dst + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                // one 256-bit store per lane: the lanes of a warp write to 32 different 128-byte lines either way
+                // (pixels are 192 B apart), so the LSU cost is per instruction, not per byte
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "l"(dst + c0), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]),
+                                "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) cv_bar_arrive(tempty);
+            if (lane == 0) cv_bar_arrive(d01_empty(it & 1u));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -299,8 +324,9 @@ extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int
     MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = 2 * (long long)n;
     const long long grid = tiles < sms ? tiles : sms;
+    const char *e = getenv("MSW_CONV_DBG");
     conv3x3_tc_kernel<<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(ma0, ma1, mw0, mw1,
-                                                                                            (__half *)y16, tiles);
+                                                                                            (__half *)y16, tiles, e ? atoi(e) : 0);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }
