@@ -475,7 +475,7 @@ def bench_rollout(torch, m, dev, rank, world, reduce_max):
     flops = 0.44e9 * N * (T + 1)                      # ~0.44 GFLOP / board / forward
     return {"workload": "C3", "frames_per_s": world * N * T / (ms / 1e3), "envs_per_gpu": N, "steps": T,
             "ms_rollout": ms_roll, "ms_gae": ms_gae,
-            "forward": "cuDNN fp16 NHWC convs + fused GroupNorm/ReLU/Dropout2d/residual kernel (msw_gn_act)",
+            "forward": "trunk 3x3 convs on tcgen05 (msw_conv3x3; the 10-channel stem conv stays cuDNN) + fused GroupNorm/ReLU/Dropout2d/residual kernel (msw_gn_act) + fused per-cell heads on tcgen05 (msw_cell_heads)",
             "model": "cnn_residual 96x5 (950,947 params), random init, train mode (dropout on, as the reference)",
             "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": episodes,
             "stock_module_forward": {"frames_per_s": world * N * T / (s_ms / 1e3), "ms_rollout": s_roll,
