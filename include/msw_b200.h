@@ -263,6 +263,18 @@ int msw_cell_heads(const void *a16, const void *w1, const void *b1, const void *
 int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
                 int32_t C, void *stream);
 
+/* msw_conv3x3 with msw_gn_act fused into its epilogue: one launch for "convolution, GroupNorm, (+ fp32
+ * residual), ReLU, Dropout2d" of a residual block half (cnn_residual.py:17-27).  Arguments as in the two
+ * calls it replaces: y16 = fp16(relu(GN(conv(x16) + conv_bias) [+ res32]) [* Dropout2d]), y32 (nullable) the
+ * same in fp32; the conv output is rounded to fp16 before the norm exactly as the unfused path (and the
+ * autocast reference) does; Dropout2d draws the same stream as msw_gn_act.  16x16 boards, C = 96, G = 6.
+ * (Round 1: correct but slower than the two calls it replaces -- see DESIGN.md 4.5c; the rollout forward
+ * uses it only with MSW_CONV_GN=1.) */
+int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
+                   const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
+                   int32_t W, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed, uint64_t call_id,
+                   const uint32_t *epoch, void *stream);
+
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and
  * Dropout2d) come from the forward call (all three nullable there, given

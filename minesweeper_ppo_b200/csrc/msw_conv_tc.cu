@@ -18,6 +18,7 @@
 // 128 x 192 x 16 and 18 of 128 x 96 x 16 per tile), warp 2 TMEM allocation, warps 4-15 epilogue (each warpgroup a
 // third of the channels).
 #include "../../include/msw_b200.h"
+#include "msw_common.cuh"
 #include "msw_error.h"
 
 #include <cuda.h>
@@ -37,8 +38,21 @@ constexpr unsigned A0_BYTES = PX_IN * 128u, A1_BYTES = PX_IN * 64u, A_STAGE = A0
 constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = OFF_W1 + W1_BYTES;
 constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], tfull, d2_empty, wfull, d01_empty[2]
 constexpr unsigned OFF_TMEM = OFF_BAR + 9 * 8u;
-constexpr unsigned SMEM_BYTES = OFF_TMEM + 16u + 1024u;                 // + slack to align the base to 1024 B
+constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;                        // GN epilogue: [2 passes][2 parity][12 warps][2 groups] f32
+constexpr unsigned OFF_CB = OFF_PART + 2 * 2 * 12 * 2 * 4u;             // [96] conv bias
+constexpr unsigned OFF_AB = OFF_CB + C * 4u;                            // [2 parity][2][96]: per-channel scale a, shift b of the board
+constexpr unsigned SMEM_BYTES = OFF_AB + 2 * 2 * C * 4u + 1024u;        // + slack to align the base to 1024 B
 }  // namespace cv
+
+// What the fused GroupNorm epilogue needs (conv3x3_tc_kernel<true>); same meaning as msw_gn_act's arguments.
+struct ConvGnParams {
+    const float *cbias, *gamma, *beta;   // [96]
+    const float *res32;                  // nullable [n][256][96]
+    float *y32;                          // nullable [n][256][96]
+    float eps, drop_p, drop_scale;
+    uint32_t k0, k1, call_lo, call_hi;
+    const uint32_t *epoch;               // nullable
+};
 
 __device__ __forceinline__ unsigned cv_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cv_bar_init(unsigned bar, unsigned count)
@@ -97,10 +111,31 @@ __device__ __forceinline__ void cv_ld16(unsigned taddr, uint32_t (&v)[16])
                  : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void cv_st256(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void cv_ld256(const void *p, uint32_t (&v)[8])
+{
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ float cv_warp_sum(float v)          // fixed shuffle tree: deterministic
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// GN = false: out = conv(x) (fp16).  GN = true: out = relu(GroupNorm(conv(x) + bias) [+ res]) [* Dropout2d], the
+// whole inter-convolution step of msw_gn_act fused into the epilogue (6 groups of 16 channels; statistics over
+// the board = the CTA's two consecutive tiles, whose fp16-rounded conv outputs wait in registers).
+template <bool GN>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
-                  __half *__restrict__ out, long long tiles, int dbg)
+                  __half *__restrict__ out, long long boards, int dbg, const __grid_constant__ ConvGnParams gp)
 {
     using namespace cv;
     extern __shared__ unsigned char smem_dyn[];
@@ -140,10 +175,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             cv_tma_2d(base + OFF_W0 + t * W0_TAP, &map_w0, 0, t * C, wfull);
             cv_tma_2d(base + OFF_W1 + t * W1_TAP, &map_w1, 64, t * C, wfull);
         }
-        unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        // a CTA takes whole boards: tiles 2*board, 2*board + 1 back to back (the GN epilogue needs both)
+        for (unsigned it = 0;; ++it) {
+            const long long board = blockIdx.x + (long long)(it >> 1) * gridDim.x;
+            if (board >= boards) break;
             const unsigned s = it % STAGES, ph = (it / STAGES) & 1u;
-            const int n = (int)(tile >> 1), y0 = (int)(tile & 1) * 8;
+            const int n = (int)board, y0 = (int)(it & 1u) * 8;
             cv_bar_wait(empty(s), ph ^ 1u);
             cv_bar_expect(full(s), A_STAGE);
             cv_tma_4d(base + OFF_A + s * A_STAGE, &map_a0, 0, 0, y0 - 1, n, full(s));
@@ -161,8 +198,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         constexpr unsigned idesc192 = (1u << 4) | ((unsigned)(2 * C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
         constexpr unsigned idesc96 = (1u << 4) | ((unsigned)(C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
         cv_bar_wait(wfull, 0);
-        unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (unsigned it = 0;; ++it) {
+            if (blockIdx.x + (long long)(it >> 1) * gridDim.x >= boards) break;
             const unsigned s = it % STAGES, ph = (it / STAGES) & 1u;
             cv_bar_wait(full(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -194,8 +231,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         // ---- epilogue: thread = pixel (TMEM lane q*32 + lane), each of the three warpgroups a third of the channels
         const int q = warp & 3, third = (warp - 4) >> 2;
         const int x = lane & 15;
-        unsigned it = 0;
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        if constexpr (!GN) {
+        for (unsigned it = 0;; ++it) {
+            const long long board = blockIdx.x + (long long)(it >> 1) * gridDim.x;
+            if (board >= boards) break;
+            const long long tile = 2 * board + (it & 1u);
             cv_bar_wait(tfull, it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned trow = tmem + ((unsigned)(q * 32) << 16) + third * 32;
@@ -243,7 +283,153 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             __syncwarp();
             if (lane == 0) cv_bar_arrive(d01_empty(it & 1u));
         }
+        } else {
+        // ---- fused GroupNorm epilogue.  Thread = pixel, its 32 channels = groups 2*third and 2*third + 1.
+        const int we = warp - 4, te = tid - 128;                        // epilogue warp 0..11 = third*4 + q, thread 0..383
+        float *s_part = reinterpret_cast<float *>(gen + OFF_PART);      // [pass][parity][warp][group]
+        float *s_cb = reinterpret_cast<float *>(gen + OFF_CB);          // conv bias
+        float *s_ab = reinterpret_cast<float *>(gen + OFF_AB);          // [parity][a | b][channel]
+        const int cbase = third * 32;
+        const uint32_t thresh = (uint32_t)(gp.drop_p * 65536.0f);
+        if (te < C) s_cb[te] = gp.cbias[te];
+        asm volatile("bar.sync 1, 384;" ::: "memory");
+        const float2 *cb2 = reinterpret_cast<const float2 *>(s_cb + cbase);
+        for (unsigned bi = 0;; ++bi) {
+            const long long board = blockIdx.x + (long long)bi * gridDim.x;
+            if (board >= boards) break;
+            const unsigned par = bi & 1u;
+            uint32_t h[2][16];                       // fp16-rounded conv output of both tiles (the reference's rounding point)
+            float gs0 = 0.0f, gs1 = 0.0f;            // sum of (x + bias) over the thread's two groups
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                cv_bar_wait(tfull, (unsigned)half);  // tile index 2*bi + half has parity `half`
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned trow = tmem + ((unsigned)(q * 32) << 16) + third * 32;
+                const unsigned d01 = trow + (unsigned)half * 2u * C, d2 = trow + 4u * C;
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t vm[16], v0[16], vp[16];
+                    cv_ld16(d01 + c0, vm);
+                    cv_ld16(d01 + C + c0, v0);
+                    cv_ld16(d2 + c0, vp);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c0 == 16) {                  // everything this tile needs from TMEM is in registers: release both buffers
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) { cv_bar_arrive(d2_empty); cv_bar_arrive(d01_empty((unsigned)half)); }
+                    }
+                    float gsum = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float r[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j + e]), 1);
+                            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j + e]), 1);
+                            r[e] = __uint_as_float(v0[j + e]) + (x > 0 ? left : 0.0f) + (x < 15 ? right : 0.0f);
+                        }
+                        const __half2 hh = __floats2half2_rn(r[0], r[1]);
+                        h[half][(c0 + j) >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
+                        const float2 f = __half22float2(hh), cb = cb2[(c0 + j) >> 1];
+                        gsum += (f.x + cb.x) + (f.y + cb.y);
+                    }
+                    if (c0 == 0) gs0 += gsum; else gs1 += gsum;
+                }
+            }
+            // ---- statistics of the board: two passes over the registers (mean, then squared deviations)
+            gs0 = cv_warp_sum(gs0);
+            gs1 = cv_warp_sum(gs1);
+            if (lane == 0) { s_part[(0 * 2 + par) * 24 + we * 2 + 0] = gs0; s_part[(0 * 2 + par) * 24 + we * 2 + 1] = gs1; }
+            asm volatile("bar.sync 1, 384;" ::: "memory");
+            float mean[2];
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+                float t = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) t += s_part[(0 * 2 + par) * 24 + (third * 4 + qq) * 2 + g2];
+                mean[g2] = t * (1.0f / 4096.0f);
+            }
+            float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h[half][jj])), cb = cb2[jj];
+                    const float m = jj < 8 ? mean[0] : mean[1];
+                    const float d0 = (f.x + cb.x) - m, d1 = (f.y + cb.y) - m;
+                    if (jj < 8) q0 = fmaf(d0, d0, fmaf(d1, d1, q0)); else q1 = fmaf(d0, d0, fmaf(d1, d1, q1));
+                }
+            q0 = cv_warp_sum(q0);
+            q1 = cv_warp_sum(q1);
+            if (lane == 0) { s_part[(1 * 2 + par) * 24 + we * 2 + 0] = q0; s_part[(1 * 2 + par) * 24 + we * 2 + 1] = q1; }
+            asm volatile("bar.sync 1, 384;" ::: "memory");
+            if (te < C) {
+                // one thread per channel folds statistics, affine, conv bias and the Dropout2d scale (msw_gn_act's
+                // stream: Philox keyed by board and 8-channel chunk) into y = a*x + b
+                const int c = te, gsel = (c >> 4) & 1, w4 = (c >> 5) * 4;
+                float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    t0 += s_part[(0 * 2 + par) * 24 + (w4 + qq) * 2 + gsel];
+                    t1 += s_part[(1 * 2 + par) * 24 + (w4 + qq) * 2 + gsel];
+                }
+                const float mg = t0 * (1.0f / 4096.0f);
+                const float rg = rsqrtf(t1 * (1.0f / 4096.0f) + gp.eps);       // biased variance, eps as torch
+                float sc = gp.drop_scale;
+                if (gp.drop_p > 0.0f) {
+                    uint32_t w[4];
+                    philox4x32_10(gp.k0, gp.k1 ^ 0x44524f50u, (uint32_t)board, (uint32_t)(board >> 32) ^ (uint32_t)(c >> 3), gp.call_lo,
+                                  gp.call_hi + (gp.epoch ? *gp.epoch : 0u), w);
+                    const int k = c & 7;
+                    const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    if (u16 < thresh) sc = 0.0f;
+                }
+                const float a = gp.gamma[c] * rg;
+                s_ab[(par * 2 + 0) * C + c] = a * sc;
+                s_ab[(par * 2 + 1) * C + c] = fmaf(s_cb[c] - mg, a, gp.beta[c]) * sc;
+            }
+            asm volatile("bar.sync 1, 384;" ::: "memory");
+            // ---- normalise, (+ residual), ReLU, store: both tiles
+            const float4 *a4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 0) * C + cbase);
+            const float4 *b4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 1) * C + cbase);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const long long px = board * 256 + half * 128 + q * 32 + lane;
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 8) {
+                    const float4 aa0 = a4[c0 >> 2], aa1 = a4[(c0 >> 2) + 1], bb0 = b4[c0 >> 2], bb1 = b4[(c0 >> 2) + 1];
+                    const float av[8] = {aa0.x, aa0.y, aa0.z, aa0.w, aa1.x, aa1.y, aa1.z, aa1.w};
+                    const float bv[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+                    uint32_t rr[8];
+                    if (gp.res32) cv_ld256(gp.res32 + px * C + cbase + c0, rr);
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h[half][(c0 + j) >> 1]));
+                        float v0 = fmaf(f.x, av[j], bv[j]), v1 = fmaf(f.y, av[j + 1], bv[j + 1]);
+                        if (gp.res32) { v0 += __uint_as_float(rr[j]); v1 += __uint_as_float(rr[j + 1]); }
+                        o[j] = __float_as_uint(fmaxf(v0, 0.0f));
+                        o[j + 1] = __float_as_uint(fmaxf(v1, 0.0f));
+                    }
+                    if (gp.y32) cv_st256(gp.y32 + px * C + cbase + c0, o);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1]));
+                        h[half][(c0 >> 1) + k] = *reinterpret_cast<const uint32_t *>(&hh);     // reuse the slot for the output
+                    }
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) packed[k] = h[half][(c0 >> 1) + k];
+                    cv_st256(out + px * C + cbase + c0, packed);
+                }
+            }
+        }
+        }
     }
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
@@ -271,18 +457,19 @@ static CvEncodeFn cv_encode_fn()
 
 }  // namespace msw
 
-extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
-                           int32_t C, void *stream)
+// Shared host side of msw_conv3x3 / msw_conv3x3_gn: argument checks, the four tensor maps, the launch.
+static int conv_launch(const char *who, const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
+                       int32_t C, const msw::ConvGnParams *gn, void *stream)
 {
     using namespace msw;
-    if (!x16 || !w_taps16 || !y16) return fail(MSW_ERR_NULL, "msw_conv3x3: NULL pointer");
+    if (!x16 || !w_taps16 || !y16) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
     if (H != 16 || W != 16 || C != cv::C)
-        return fail(MSW_ERR_BAD_SHAPE, "msw_conv3x3: only 16x16 boards with 96 channels (got %dx%d, C=%d)", H, W, C);
-    if (n < 0 || n > 0x3fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_conv3x3: n=%lld", (long long)n);
-    if ((((uintptr_t)x16 | (uintptr_t)w_taps16 | (uintptr_t)y16) & 15u) != 0)
-        return fail(MSW_ERR_ALIGN, "msw_conv3x3: tensors must be 16-byte aligned");
+        return fail(MSW_ERR_BAD_SHAPE, "%s: only 16x16 boards with 96 channels (got %dx%d, C=%d)", who, H, W, C);
+    if (n < 0 || n > 0x3fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "%s: n=%lld", who, (long long)n);
+    if ((((uintptr_t)x16 | (uintptr_t)w_taps16 | (uintptr_t)y16) & 31u) != 0)
+        return fail(MSW_ERR_ALIGN, "%s: tensors must be 32-byte aligned", who);
     if (n == 0) return MSW_OK;
-    if (!cv_encode_fn()) return fail(MSW_ERR_ARG, "msw_conv3x3: cuTensorMapEncodeTiled is not available");
+    if (!cv_encode_fn()) return fail(MSW_ERR_ARG, "%s: cuTensorMapEncodeTiled is not available", who);
     CUtensorMap ma0, ma1, mw0, mw1;
     {
         // activation [n][16][16][96] fp16: dims innermost first
@@ -297,7 +484,7 @@ extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int
                                            box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS)
-            return fail(MSW_ERR_ARG, "msw_conv3x3: activation tensor map failed (%d, %d)", (int)r0, (int)r1);
+            return fail(MSW_ERR_ARG, "%s: activation tensor map failed (%d, %d)", who, (int)r0, (int)r1);
     }
     {
         // weights [9 taps * 96 co][96 ci] fp16
@@ -312,21 +499,53 @@ extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int
                                            box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS)
-            return fail(MSW_ERR_ARG, "msw_conv3x3: weight tensor map failed (%d, %d)", (int)r0, (int)r1);
+            return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
     }
     static thread_local bool configured = false;
     if (!configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv::SMEM_BYTES));
+        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv::SMEM_BYTES));
+        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv::SMEM_BYTES));
         configured = true;
     }
     int dev = 0, sms = 0;
     MSW_CUDA_TRY(cudaGetDevice(&dev));
     MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long tiles = 2 * (long long)n;
-    const long long grid = tiles < sms ? tiles : sms;
+    const long long grid = n < sms ? n : sms;                       // persistent: whole boards per CTA
     const char *e = getenv("MSW_CONV_DBG");
-    conv3x3_tc_kernel<<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(ma0, ma1, mw0, mw1,
-                                                                                            (__half *)y16, tiles, e ? atoi(e) : 0);
+    ConvGnParams none = {};
+    if (gn)
+        conv3x3_tc_kernel<true><<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(
+            ma0, ma1, mw0, mw1, (__half *)y16, (long long)n, 0, *gn);
+    else
+        conv3x3_tc_kernel<false><<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(
+            ma0, ma1, mw0, mw1, (__half *)y16, (long long)n, e ? atoi(e) : 0, none);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
+}
+
+extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
+                           int32_t C, void *stream)
+{
+    return conv_launch("msw_conv3x3", x16, w_taps16, y16, n, H, W, C, nullptr, stream);
+}
+
+extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
+                              const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
+                              int32_t W, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed, uint64_t call_id,
+                              const uint32_t *epoch, void *stream)
+{
+    using namespace msw;
+    if (!conv_bias || !gamma || !beta) return fail(MSW_ERR_NULL, "msw_conv3x3_gn: NULL pointer");
+    if (G != 6) return fail(MSW_ERR_BAD_SHAPE, "msw_conv3x3_gn: needs 6 groups of 16 channels (G=%d)", G);
+    if (drop_p < 0.0f || drop_p >= 1.0f) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: drop_p=%f", drop_p);
+    if (drop_p > 0.0f && res32) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: dropout is only defined on the no-residual path");
+    if ((((uintptr_t)res32 | (uintptr_t)y32) & 31u) != 0)
+        return fail(MSW_ERR_ALIGN, "msw_conv3x3_gn: res32 / y32 must be 32-byte aligned");
+    ConvGnParams g;
+    g.cbias = conv_bias; g.gamma = gamma; g.beta = beta; g.res32 = res32; g.y32 = y32;
+    g.eps = eps; g.drop_p = drop_p; g.drop_scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.call_lo = (uint32_t)call_id; g.call_hi = (uint32_t)(call_id >> 32);
+    g.epoch = epoch;
+    return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, C, &g, stream);
 }

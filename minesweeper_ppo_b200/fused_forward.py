@@ -93,6 +93,34 @@ def conv3x3(x16: torch.Tensor, taps16: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def conv3x3_gn(x16: torch.Tensor, taps16: torch.Tensor, norm: torch.nn.GroupNorm, conv_bias: torch.Tensor, *,
+               res32: Optional[torch.Tensor] = None, drop_p: float = 0.0, want32: bool = False, seed: int = 0,
+               call_id: int = 0, epoch: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """msw_conv3x3_gn = `gn_act(conv3x3(x16, taps16), norm, conv_bias=..., ...)` in one launch."""
+    L = _lib.load()
+    N, C, H, W = x16.shape
+    if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("conv3x3_gn: x must be fp16 channels_last")
+    if taps16.dtype != torch.float16 or tuple(taps16.shape) != (9, C, C) or not taps16.is_contiguous():
+        raise ValueError("conv3x3_gn: taps must be contiguous fp16 [9, C, C]")
+    if res32 is not None and (res32.dtype != torch.float32 or tuple(res32.shape) != (N, C, H, W)
+                              or not res32.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("conv3x3_gn: residual must be fp32 channels_last of the same shape")
+    dev = x16.device
+    y16 = torch.empty_like(x16, memory_format=torch.channels_last)
+    y32 = (torch.empty((N, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+           if want32 else None)
+    with torch.cuda.device(dev):
+        rc = L.msw_conv3x3_gn(x16.data_ptr(), taps16.data_ptr(), conv_bias.data_ptr(),
+                              None if res32 is None else res32.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(),
+                              y16.data_ptr(), None if y32 is None else y32.data_ptr(), N, H, W, C, norm.num_groups,
+                              float(norm.eps), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                              int(call_id) & 0xFFFFFFFFFFFFFFFF, None if epoch is None else epoch.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "msw_conv3x3_gn")
+    return y16, y32
+
+
 class FusedRolloutForward:
     """Callable with the module's `(obs, return_mine)` signature, for use under torch.no_grad()."""
 
@@ -177,17 +205,26 @@ class FusedRolloutForward:
         last = len(self.blocks) - 1
         pooled = None
         own_conv = self.taps is not None and tuple(a16.shape[2:]) == (16, 16)
+        # msw_conv3x3_gn (GroupNorm fused into the conv epilogue) is correct but, in round 1, issue-bound in its
+        # epilogue and slower than the two kernels it replaces (6.37 vs 6.04 ms per forward): opt-in
+        fuse_gn = own_conv and m.stem[1].num_groups == 6 and os.environ.get("MSW_CONV_GN", "0") == "1"
         for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
-            c1 = conv3x3(a16, self.taps[k][0]) if own_conv else F.conv2d(a16, w1, None, padding=1)
-            t16, _ = gn_act(c1, blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed,
-                            call_id=cid + k, epoch=self.epoch)
+            if fuse_gn:                  # conv + GroupNorm + ReLU + Dropout2d in one launch
+                t16, _ = conv3x3_gn(a16, self.taps[k][0], blk.norm1, b1, drop_p=p, seed=self.seed, call_id=cid + k,
+                                    epoch=self.epoch)
+            else:
+                c1 = conv3x3(a16, self.taps[k][0]) if own_conv else F.conv2d(a16, w1, None, padding=1)
+                t16, _ = gn_act(c1, blk.norm1, conv_bias=b1, drop_p=p, seed=self.seed, call_id=cid + k, epoch=self.epoch)
             if k == last:
                 # nothing reads the fp32 residual stream after the last block except the value head's
-                # AdaptiveAvgPool2d(1): the kernel emits that mean instead of writing y32
+                # AdaptiveAvgPool2d(1): msw_gn_act emits that mean instead of writing y32 (unfused call)
                 pooled = torch.empty((a16.shape[0], a16.shape[1]), dtype=torch.float32, device=a16.device)
-            c2 = conv3x3(t16, self.taps[k][1]) if own_conv else F.conv2d(t16, w2, None, padding=1)
-            a16, a32 = gn_act(c2, blk.norm2, conv_bias=b2, res32=a32, want32=k != last, pool32=pooled)
+            if fuse_gn and k != last:    # conv + GroupNorm + residual add + ReLU in one launch
+                a16, a32 = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want32=True)
+            else:
+                c2 = conv3x3(t16, self.taps[k][1]) if own_conv else F.conv2d(t16, w2, None, padding=1)
+                a16, a32 = gn_act(c2, blk.norm2, conv_bias=b2, res32=a32, want32=k != last, pool32=pooled)
         n, c, h, w = a16.shape
         rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
         if pooled is None:                                           # no residual blocks

@@ -205,6 +205,37 @@ def test_conv3x3_matches_cudnn(n):
             assert torch.equal(one, ref), (ky, kx)
 
 
+@pytest.mark.parametrize("n,res,drop", [(3, False, 0.0), (149, True, 0.0), (300, False, 0.25), (7, True, 0.0)])
+def test_conv3x3_gn_matches_unfused(n, res, drop):
+    """msw_conv3x3_gn vs msw_conv3x3 followed by msw_gn_act on the same operands: same fp16 rounding point of
+    the conv output, same Dropout2d stream; the group statistics are reduced in a different order, so the fp32
+    output agrees to a few ulp and the fp16 one to one fp16 ulp."""
+    import torch
+    from minesweeper_ppo_b200.fused_forward import conv3x3, conv3x3_gn, conv3x3_taps, gn_act
+    g = torch.Generator(device="cuda").manual_seed(n)
+    C = 96
+    x = torch.randn((n, C, 16, 16), device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((C, C, 3, 3), device="cuda", generator=g) / (9 * C) ** 0.5).half()
+    bias = 0.2 * torch.randn((C,), device="cuda", generator=g)
+    norm = torch.nn.GroupNorm(6, C).cuda()
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5); norm.bias.uniform_(-0.3, 0.3)
+    r = (torch.randn((n, C, 16, 16), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+         if res else None)
+    taps = conv3x3_taps(w)
+    want16, want32 = gn_act(conv3x3(x, taps), norm, conv_bias=bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
+    got16, got32 = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
+    again16, again32 = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
+    assert torch.equal(got16, again16) and torch.equal(got32, again32)
+    scale = float(want32.abs().max()) + 1.0
+    assert float((got32 - want32).abs().max()) <= 2e-5 * scale
+    assert float((got16.float() - want16.float()).abs().max()) <= 2e-3 * scale
+    if drop > 0:                                             # the same channels are dropped
+        assert torch.equal(got32.abs().sum(dim=(2, 3)) == 0, want32.abs().sum(dim=(2, 3)) == 0)
+    only16, none = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=False, seed=5, call_id=77)
+    assert none is None and torch.equal(only16, got16)
+
+
 def test_gn_act_pooled_output():
     """msw_gn_act pool32 = spatial mean of the fp32 output, with and without writing y32."""
     import torch
