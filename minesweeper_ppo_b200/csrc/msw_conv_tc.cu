@@ -3,20 +3,22 @@
 // 5th-generation tensor cores.
 //
 // out[y][x][co] = sum_{dy,dx,ci} in[y+dy][x+dx][ci] * w[co][ci][dy][dx] is computed as nine shifted GEMMs
-// per 128-pixel tile (8 image rows of one board), with the two kinds of shift handled where they are free:
-//   * vertical: the tile's input rows y0-1 .. y0+8 sit in shared memory as ONE linear [160 pixel][96 ch]
-//     block (a single 4-D TMA box; rows above / below the board are zero-filled by the tensor map), so the A
-//     operand of tap dy is the same block at a byte offset of (dy+1) * 16 pixels -- a multiple of the swizzle
-//     period, i.e. just another shared-memory descriptor;
-//   * horizontal: tap dx accumulates into its own TMEM accumulator D_dx WITHOUT shifting the pixels, and the
-//     epilogue forms out[y][x] = D_-1[y][x-1] + D_0[y][x] + D_+1[y][x+1].  A thread owns one pixel (TMEM lane),
-//     a warp owns two image rows, so x-1 / x+1 are the neighbouring lanes (one shuffle each) and the board
-//     edge coincides with the lanes that have no neighbour.
+// per 128-pixel tile (8 image rows of one board) that all accumulate into ONE TMEM accumulator.  The tile's
+// input rows y0-1 .. y0+8 sit in shared memory as one linear [160 pixel][96 ch] block (a single 4-D TMA box;
+// rows above / below the board are zero-filled by the tensor map), and a tap is nothing but a different
+// shared-memory descriptor on that block:
+//   * the A operand of tap (dy, dx) starts (dy+1) * 16 + dx pixels into the block.  The swizzle is a function
+//     of the absolute shared-memory address (measured: descriptors whose start is shifted by whole 128- or
+//     64-byte rows give exact results with the matrix base offset left at 0), so no second copy and no im2col;
+//   * a horizontal shift drags the neighbouring image row's edge pixel into the rows with x = 0 (dx = -1) or
+//     x = 15 (dx = +1); those rows of D are switched off for that tap with tcgen05.mma's disable-output-lane
+//     mask, which is exactly the zero padding.  The first tap issued is the unmasked centre column, so every
+//     row of the accumulator is initialised.
 // All nine [96 x 96] weight taps stay resident in shared memory (162 KB, loaded once per persistent CTA);
 // the activation streams through a 2-stage ring.  K = 96 = one 64-channel block (128-byte swizzle) + one
-// 32-channel block (64-byte swizzle).  Roles: warp 0 TMA producer, warp 1 MMA issuer (18 tcgen05.mma of
-// 128 x 192 x 16 and 18 of 128 x 96 x 16 per tile), warp 2 TMEM allocation, warps 4-15 epilogue (each warpgroup a
-// third of the channels).
+// 32-channel block (64-byte swizzle).  Roles: warp 0 TMA producer, warp 1 MMA issuer (54 tcgen05.mma of
+// 128 x 96 x 16 per tile into a ring of four 96-column accumulators), warp 2 TMEM allocation, warps 4-15
+// epilogue (thread = pixel, each warpgroup a third of the channels).
 #include "../../include/msw_b200.h"
 #include "msw_common.cuh"
 #include "msw_error.h"
@@ -36,8 +38,9 @@ constexpr unsigned W0_TAP = C * 128u, W1_TAP = C * 64u;                 // bytes
 constexpr unsigned W0_BYTES = 9 * W0_TAP, W1_BYTES = 9 * W1_TAP;
 constexpr unsigned A0_BYTES = PX_IN * 128u, A1_BYTES = PX_IN * 64u, A_STAGE = A0_BYTES + A1_BYTES;
 constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = OFF_W1 + W1_BYTES;
-constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], tfull, d2_empty, wfull, d01_empty[2]
-constexpr unsigned OFF_TMEM = OFF_BAR + 9 * 8u;
+constexpr int ACC = 4;                                                   // accumulator ring: 4 x 96 TMEM columns
+constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], wfull, tfull[4], tempty[4]
+constexpr unsigned OFF_TMEM = OFF_BAR + 13 * 8u;
 constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;                        // GN epilogue: [2 passes][2 parity][12 warps][2 groups] f32
 constexpr unsigned OFF_CB = OFF_PART + 2 * 2 * 12 * 2 * 4u;             // [96] conv bias
 constexpr unsigned OFF_AB = OFF_CB + C * 4u;                            // [2 parity][2][96]: per-channel scale a, shift b of the board
@@ -99,6 +102,13 @@ __device__ __forceinline__ void cv_mma(unsigned d_tmem, uint64_t a, uint64_t b, 
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
                  :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the disable-output-lane mask: bit i of word w set = row 32w + i of D is not written
+__device__ __forceinline__ void cv_mma_masked(unsigned d_tmem, uint64_t a, uint64_t b, unsigned idesc, unsigned accumulate,
+                                              unsigned mask)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p; }"
+                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(mask) : "memory");
+}
 __device__ __forceinline__ void cv_commit(unsigned bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -144,17 +154,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const unsigned bars = base + OFF_BAR;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (2 + s); };
-    const unsigned tfull = bars + 8u * 4, d2_empty = bars + 8u * 5, wfull = bars + 8u * 6;
-    auto d01_empty = [&](unsigned b) { return bars + 8u * (7 + b); };
+    const unsigned wfull = bars + 8u * 4;
+    auto tfull = [&](unsigned a) { return bars + 8u * (5 + a); };
+    auto tempty = [&](unsigned a) { return bars + 8u * (9 + a); };
     volatile uint32_t *s_tmem = reinterpret_cast<volatile uint32_t *>(gen + OFF_TMEM);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { cv_bar_init(full(s), 1); cv_bar_init(empty(s), 1); }
-        cv_bar_init(tfull, 1);
-        cv_bar_init(d2_empty, 12);
-        cv_bar_init(d01_empty(0), 12);
-        cv_bar_init(d01_empty(1), 12);
+        for (unsigned a = 0; a < ACC; ++a) { cv_bar_init(tfull(a), 1); cv_bar_init(tempty(a), 12); }
         cv_bar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -187,101 +195,76 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             cv_tma_4d(base + OFF_A + s * A_STAGE + A0_BYTES, &map_a1, 64, 0, y0 - 1, n, full(s));
         }
     } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer.  idesc: D = F32, A = B = F16, K-major, M = 128, N = 192 or 96.
-        // One MMA covers the taps dx = -1 and dx = 0 together (their weight blocks are adjacent in shared memory
-        // and their accumulators adjacent in TMEM, N = 192), a second one dx = +1 (N = 96): with three N = 96
-        // MMAs the A operand is read from shared memory three times and the tensor pipe waits for it (7 KB of
-        // operands per 48-cycle MMA > 128 B/clk).  TMEM: D_-1|D_0 double buffered at columns 0 / 192, D_+1 single
-        // buffered at 384 (2 x 288 columns do not fit).  The epilogue copies its D_+1 values to registers first
-        // and releases that buffer at once, so the N = 96 MMAs of the next tile wait for one TMEM load, not for
-        // the whole epilogue; the N = 192 MMAs only need the epilogue of the tile before the previous one.
-        constexpr unsigned idesc192 = (1u << 4) | ((unsigned)(2 * C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
-        constexpr unsigned idesc96 = (1u << 4) | ((unsigned)(C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
+        // ---- MMA issuer.  idesc: D = F32, A = B = F16, K-major, M = 128, N = 96.
+        constexpr unsigned idesc = (1u << 4) | ((unsigned)(C >> 3) << 17) | ((unsigned)(TILE_PX >> 4) << 24);
         cv_bar_wait(wfull, 0);
         for (unsigned it = 0;; ++it) {
             if (blockIdx.x + (long long)(it >> 1) * gridDim.x >= boards) break;
-            const unsigned s = it % STAGES, ph = (it / STAGES) & 1u;
+            const unsigned s = it % STAGES, ph = (it / STAGES) & 1u, acc = it % ACC, aph = (it / ACC) & 1u;
+            cv_bar_wait(tempty(acc), aph ^ 1u);                   // the epilogue has drained this accumulator
             cv_bar_wait(full(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned a0 = base + OFF_A + s * A_STAGE, a1 = a0 + A0_BYTES;
+            const unsigned a0 = base + OFF_A + s * A_STAGE, a1 = a0 + A0_BYTES, d = tmem + acc * C;
+            unsigned accumulate = 0u;
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                // part 0 reuses the D_-1|D_0 buffer of tile it-2, part 1 the D_+1 buffer of tile it-1
-                cv_bar_wait(part == 0 ? d01_empty(it & 1u) : d2_empty, part == 0 ? ((it >> 1) & 1u) ^ 1u : (it & 1u) ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned d = part == 0 ? tmem + (it & 1u) * 2u * C : tmem + 4u * C;
-                const unsigned idesc = part == 0 ? idesc192 : idesc96;
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int tap = dy * 3 + 2 * part;                       // first weight block of this MMA
+                for (int o = 0; o < 3; ++o) {
+                    const int dxi = o == 0 ? 1 : o == 1 ? 0 : 2;           // the unmasked centre tap first
+                    const int tap = dy * 3 + dxi;
+                    // rows of D whose horizontal neighbour is off the board: x = 0 for dx = -1, x = 15 for dx = +1
+                    const unsigned mask = dxi == 0 ? 0x00010001u : dxi == 2 ? 0x80008000u : 0u;
+                    const unsigned sa0 = a0 + (unsigned)((dy * HW_W + dxi - 1) * 128), sa1 = a1 + (unsigned)((dy * HW_W + dxi - 1) * 64);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                              // channels 0..63: four 16-channel steps
-                        cv_mma(d, cv_desc128(a0 + dy * HW_W * 128u) + 2u * k, cv_desc128(base + OFF_W0 + tap * W0_TAP) + 2u * k,
-                               idesc, (dy | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {                            // channels 0..63: four 16-channel steps
+                        cv_mma_masked(d, cv_desc128(sa0) + 2u * k, cv_desc128(base + OFF_W0 + tap * W0_TAP) + 2u * k, idesc,
+                                      accumulate, mask);
+                        accumulate = 1u;
+                    }
 #pragma unroll
                     for (int k = 0; k < 2; ++k)                              // channels 64..95
-                        cv_mma(d, cv_desc64(a1 + dy * HW_W * 64u) + 2u * k, cv_desc64(base + OFF_W1 + tap * W1_TAP) + 2u * k,
-                               idesc, 1u);
+                        cv_mma_masked(d, cv_desc64(sa1) + 2u * k, cv_desc64(base + OFF_W1 + tap * W1_TAP) + 2u * k, idesc, 1u, mask);
                 }
-            }
-            cv_commit(empty(s));
-            cv_commit(tfull);
+            cv_commit(empty(s));             // the smem stage is free once these MMAs have read it
+            cv_commit(tfull(acc));           // ... and the accumulator is complete
         }
     } else if (warp >= 4) {
         // ---- epilogue: thread = pixel (TMEM lane q*32 + lane), each of the three warpgroups a third of the channels
         const int q = warp & 3, third = (warp - 4) >> 2;
-        const int x = lane & 15;
         if constexpr (!GN) {
         for (unsigned it = 0;; ++it) {
             const long long board = blockIdx.x + (long long)(it >> 1) * gridDim.x;
             if (board >= boards) break;
-            const long long tile = 2 * board + (it & 1u);
-            cv_bar_wait(tfull, it & 1u);
+            const unsigned acc = it % ACC, aph = (it / ACC) & 1u;
+            cv_bar_wait(tfull(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned trow = tmem + ((unsigned)(q * 32) << 16) + third * 32;
-            const unsigned d01 = trow + (it & 1u) * 2u * C, d2 = trow + 4u * C;
-            __half *dst = out + ((tile >> 1) * 256 + (tile & 1) * 128 + q * 32 + lane) * (long long)C + third * 32;
-            uint32_t vp[32];                       // D_+1 (contributes to the pixel on its left): copy out, release
+            uint32_t v[32];
             {
                 uint32_t lo[16], hi[16];
-                cv_ld16(d2, lo);
-                cv_ld16(d2 + 16, hi);
+                const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + acc * C + third * 32;
+                cv_ld16(taddr, lo);
+                cv_ld16(taddr + 16, hi);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { vp[j] = lo[j]; vp[16 + j] = hi[j]; }
+                for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = hi[j]; }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) cv_bar_arrive(d2_empty);
+            if (lane == 0) cv_bar_arrive(tempty(acc));       // the accumulator is in registers: release it
+            if (dbg & 1) continue;
+            __half *dst = out + (board * 256 + (it & 1u) * 128 + q * 32 + lane) * (long long)C + third * 32;
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 16) {
-                if (dbg & 1) break;
-                uint32_t vm[16], v0[16];
-                cv_ld16(d01 + c0, vm);             // D_-1: contributes to the pixel on its right
-                cv_ld16(d01 + C + c0, v0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 uint32_t packed[8];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float r[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j + e]), 1);
-                        const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[c0 + j + e]), 1);
-                        r[e] = __uint_as_float(v0[j + e]) + (x > 0 ? left : 0.0f) + (x < 15 ? right : 0.0f);
-                    }
-                    const __half2 h = __floats2half2_rn(r[0], r[1]);
-                    packed[j >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                for (int k = 0; k < 8; ++k) {
+                    const __half2 hh = __floats2half2_rn(__uint_as_float(v[c0 + 2 * k]), __uint_as_float(v[c0 + 2 * k + 1]));
+                    packed[k] = *reinterpret_cast<const uint32_t *>(&hh);
                 }
                 // one 256-bit store per lane: the lanes of a warp write to 32 different 128-byte lines either way
                 // (pixels are 192 B apart), so the LSU cost is per instruction, not per byte
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                             :: "l"(dst + c0), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]),
-                                "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
+                cv_st256(dst + c0, packed);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) cv_bar_arrive(d01_empty(it & 1u));
         }
         } else {
         // ---- fused GroupNorm epilogue.  Thread = pixel, its 32 channels = groups 2*third and 2*third + 1.
@@ -302,38 +285,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             float gs0 = 0.0f, gs1 = 0.0f;            // sum of (x + bias) over the thread's two groups
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                cv_bar_wait(tfull, (unsigned)half);  // tile index 2*bi + half has parity `half`
+                const unsigned it = 2u * bi + half, acc = it % ACC, aph = (it / ACC) & 1u;
+                if (gp.res32)     // this pixel's 128-byte line of the residual stream: on its way to L2 while the tile is drained
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(gp.res32 + (board * 256 + half * 128 + q * 32 + lane) * (long long)C + cbase));
+                cv_bar_wait(tfull(acc), aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned trow = tmem + ((unsigned)(q * 32) << 16) + third * 32;
-                const unsigned d01 = trow + (unsigned)half * 2u * C, d2 = trow + 4u * C;
+                uint32_t lo[16], hi[16];
+                const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + acc * C + third * 32;
+                cv_ld16(taddr, lo);
+                cv_ld16(taddr + 16, hi);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) cv_bar_arrive(tempty(acc));
 #pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    uint32_t vm[16], v0[16], vp[16];
-                    cv_ld16(d01 + c0, vm);
-                    cv_ld16(d01 + C + c0, v0);
-                    cv_ld16(d2 + c0, vp);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c0 == 16) {                  // everything this tile needs from TMEM is in registers: release both buffers
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) { cv_bar_arrive(d2_empty); cv_bar_arrive(d01_empty((unsigned)half)); }
-                    }
-                    float gsum = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float r[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j + e]), 1);
-                            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j + e]), 1);
-                            r[e] = __uint_as_float(v0[j + e]) + (x > 0 ? left : 0.0f) + (x < 15 ? right : 0.0f);
-                        }
-                        const __half2 hh = __floats2half2_rn(r[0], r[1]);
-                        h[half][(c0 + j) >> 1] = *reinterpret_cast<const uint32_t *>(&hh);
-                        const float2 f = __half22float2(hh), cb = cb2[(c0 + j) >> 1];
-                        gsum += (f.x + cb.x) + (f.y + cb.y);
-                    }
-                    if (c0 == 0) gs0 += gsum; else gs1 += gsum;
+                for (int jj = 0; jj < 16; ++jj) {
+                    const uint32_t *src = jj < 8 ? lo : hi;
+                    const __half2 hh = __floats2half2_rn(__uint_as_float(src[(2 * jj) & 15]), __uint_as_float(src[(2 * jj + 1) & 15]));
+                    h[half][jj] = *reinterpret_cast<const uint32_t *>(&hh);
+                    const float2 f = __half22float2(hh), cb = cb2[jj];
+                    if (jj < 8) gs0 += (f.x + cb.x) + (f.y + cb.y); else gs1 += (f.x + cb.x) + (f.y + cb.y);
                 }
             }
             // ---- statistics of the board: two passes over the registers (mean, then squared deviations)
@@ -392,6 +363,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // ---- normalise, (+ residual), ReLU, store: both tiles
             const float4 *a4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 0) * C + cbase);
             const float4 *b4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 1) * C + cbase);
+            uint32_t rnext[8];                       // residual values of the next 8-channel chunk: loaded one chunk ahead
+            if (gp.res32) cv_ld256(gp.res32 + (board * 256 + q * 32 + lane) * (long long)C + cbase, rnext);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const long long px = board * 256 + half * 128 + q * 32 + lane;
@@ -401,7 +374,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     const float av[8] = {aa0.x, aa0.y, aa0.z, aa0.w, aa1.x, aa1.y, aa1.z, aa1.w};
                     const float bv[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
                     uint32_t rr[8];
-                    if (gp.res32) cv_ld256(gp.res32 + px * C + cbase + c0, rr);
+                    if (gp.res32) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) rr[k] = rnext[k];
+                        if (c0 < 24) cv_ld256(gp.res32 + px * C + cbase + c0 + 8, rnext);
+                        else if (half == 0) cv_ld256(gp.res32 + (px + 128) * C + cbase, rnext);
+                    }
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {

@@ -205,12 +205,14 @@ class FusedRolloutForward:
         last = len(self.blocks) - 1
         pooled = None
         own_conv = self.taps is not None and tuple(a16.shape[2:]) == (16, 16)
-        # msw_conv3x3_gn (GroupNorm fused into the conv epilogue) is correct but, in round 1, issue-bound in its
-        # epilogue and slower than the two kernels it replaces (6.37 vs 6.04 ms per forward): opt-in
-        fuse_gn = own_conv and m.stem[1].num_groups == 6 and os.environ.get("MSW_CONV_GN", "0") == "1"
+        # msw_conv3x3_gn (GroupNorm fused into the conv epilogue).  Measured per layer at 8,192 boards: without a
+        # residual 335 us fused vs 239 + 165 us; with the residual stream ~760 us fused vs 239 + 421 us (the
+        # thread-per-pixel epilogue reads / writes the fp32 stream uncoalesced).  MSW_CONV_GN: 1 (default) fuses
+        # the first half of every block, 2 both halves, 0 none.
+        gn_mode = int(os.environ.get("MSW_CONV_GN", "1")) if own_conv and m.stem[1].num_groups == 6 else 0
         for k, (blk, ((w1, b1), (w2, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             p = float(blk.dropout.p) if (m.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
-            if fuse_gn:                  # conv + GroupNorm + ReLU + Dropout2d in one launch
+            if gn_mode >= 1:             # conv + GroupNorm + ReLU + Dropout2d in one launch
                 t16, _ = conv3x3_gn(a16, self.taps[k][0], blk.norm1, b1, drop_p=p, seed=self.seed, call_id=cid + k,
                                     epoch=self.epoch)
             else:
@@ -220,7 +222,7 @@ class FusedRolloutForward:
                 # nothing reads the fp32 residual stream after the last block except the value head's
                 # AdaptiveAvgPool2d(1): msw_gn_act emits that mean instead of writing y32 (unfused call)
                 pooled = torch.empty((a16.shape[0], a16.shape[1]), dtype=torch.float32, device=a16.device)
-            if fuse_gn and k != last:    # conv + GroupNorm + residual add + ReLU in one launch
+            if gn_mode >= 2 and k != last:   # conv + GroupNorm + residual add + ReLU in one launch
                 a16, a32 = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want32=True)
             else:
                 c2 = conv3x3(t16, self.taps[k][1]) if own_conv else F.conv2d(t16, w2, None, padding=1)
