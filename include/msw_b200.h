@@ -243,6 +243,11 @@ int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
                const uint32_t *epoch, float *save_mean, float *save_rstd,
                uint8_t *save_mask, float *pool32, void *stream);
 
+/* Input of the stem convolution: fp32 NCHW observation planes obs [n][Cin][HW] (Cin <= 16; the env's 10
+ * planes) -> fp16 NHWC out16 [n][HW][16] with the missing channels zero, i.e. the autocast cast of
+ * train_rl.py:222 and the channel padding the tensor-core convolution needs, in one pass. */
+int msw_pack_obs16(const float *obs, void *out16, int64_t n, int32_t Cin, int32_t HW, void *stream);
+
 /* Both per-cell heads of CNNResidualPolicy (cnn_residual.py:57-62, 73-77,
  * 87-94: 1x1 conv C->C, ReLU, 1x1 conv C->1, for the policy and for the mine
  * belief) in one launch over the fp16 NHWC trunk activation a16 [rows][C],
@@ -256,12 +261,13 @@ int msw_cell_heads(const void *a16, const void *w1, const void *b1, const void *
                    const void *b2, void *out_policy, void *out_mine, int64_t rows,
                    int32_t C, void *stream);
 
-/* 3x3 "same" convolution of the residual trunk (cnn_residual.py:10-13: Conv2d(C, C, 3, padding=1)) on the
- * tcgen05 tensor cores, for the shape the medium config uses: 16x16 boards, C = 96.  x16: fp16 NHWC
- * [n][16][16][C]; w_taps16: fp16 [9][C_out][C_in], tap = ky*3 + kx of the module's [C_out][C_in][3][3]
- * weight; y16: fp16 NHWC conv output WITHOUT bias (msw_gn_act adds it), fp32 accumulation. */
+/* 3x3 "same" convolution of the policy trunk (cnn_residual.py:10-13: Conv2d(C, C, 3, padding=1); :50: the
+ * stem Conv2d(10, C, 3, padding=1) on the 16-channel input of msw_pack_obs16) on the tcgen05 tensor cores, for
+ * the shape the medium config uses: 16x16 boards, C = 96, Cin = 96 or 16.  x16: fp16 NHWC [n][16][16][Cin];
+ * w_taps16: fp16 [9][C][Cin], tap = ky*3 + kx of the module's [C][Cin][3][3] weight (zero for padded input
+ * channels); y16: fp16 NHWC conv output WITHOUT bias (msw_gn_act adds it), fp32 accumulation. */
 int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
-                int32_t C, void *stream);
+                int32_t Cin, int32_t C, void *stream);
 
 /* msw_conv3x3 with msw_gn_act fused into its epilogue: one launch for "convolution, GroupNorm, (+ fp32
  * residual), ReLU, Dropout2d" of a residual block half (cnn_residual.py:17-27).  Arguments as in the two
@@ -272,8 +278,8 @@ int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int
  * uses it only with MSW_CONV_GN=1.) */
 int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
                    const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
-                   int32_t W, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed, uint64_t call_id,
-                   const uint32_t *epoch, void *stream);
+                   int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed,
+                   uint64_t call_id, const uint32_t *epoch, void *stream);
 
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and

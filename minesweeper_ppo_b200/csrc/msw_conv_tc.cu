@@ -32,19 +32,31 @@
 namespace msw {
 
 namespace cv {
-constexpr int C = 96, HW_W = 16, TILE_PX = 128, ROWS_IN = 10, PX_IN = ROWS_IN * HW_W;   // 160 staged pixels
+constexpr int C = 96, HW_W = 16, TILE_PX = 128, ROWS_IN = 10, PX_IN = ROWS_IN * HW_W;   // C = output channels; 160 staged pixels
 constexpr int THREADS = 512, STAGES = 2, TMEM_COLS = 512;       // 4 control warps + 12 epilogue warps
-constexpr unsigned W0_TAP = C * 128u, W1_TAP = C * 64u;                 // bytes per tap: 64-ch block, 32-ch block
-constexpr unsigned W0_BYTES = 9 * W0_TAP, W1_BYTES = 9 * W1_TAP;
-constexpr unsigned A0_BYTES = PX_IN * 128u, A1_BYTES = PX_IN * 64u, A_STAGE = A0_BYTES + A1_BYTES;
-constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = OFF_W1 + W1_BYTES;
 constexpr int ACC = 4;                                                   // accumulator ring: 4 x 96 TMEM columns
-constexpr unsigned OFF_BAR = OFF_A + STAGES * A_STAGE;                  // full[2], empty[2], wfull, tfull[4], tempty[4]
-constexpr unsigned OFF_TMEM = OFF_BAR + 13 * 8u;
-constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;                        // GN epilogue: [2 passes][2 parity][12 warps][2 groups] f32
-constexpr unsigned OFF_CB = OFF_PART + 2 * 2 * 12 * 2 * 4u;             // [96] conv bias
-constexpr unsigned OFF_AB = OFF_CB + C * 4u;                            // [2 parity][2][96]: per-channel scale a, shift b of the board
-constexpr unsigned SMEM_BYTES = OFF_AB + 2 * 2 * C * 4u + 1024u;        // + slack to align the base to 1024 B
+
+// Shared-memory plan for CIN input channels.  CIN = 96: K = one 64-channel block (128-byte rows, 128-byte
+// swizzle) + one 32-channel block (64-byte rows, 64-byte swizzle).  CIN = 16 (the stem, observation planes padded
+// to 16): one 16-channel block (32-byte rows, 32-byte swizzle), one k-step per tap.
+template <int CIN>
+struct Cfg {
+    static_assert(CIN == 96 || CIN == 16, "supported input widths");
+    static constexpr unsigned ROW0 = CIN == 96 ? 128u : 32u, ROW1 = CIN == 96 ? 64u : 0u;     // bytes per pixel row
+    static constexpr int KS0 = CIN == 96 ? 4 : 1, KS1 = CIN == 96 ? 2 : 0;                    // 16-channel k-steps
+    static constexpr int BOX0 = CIN == 96 ? 64 : 16, BOX1 = 32;                               // TMA box widths (channels)
+    static constexpr unsigned W0_TAP = C * ROW0, W1_TAP = C * ROW1;     // bytes per weight tap
+    static constexpr unsigned W0_BYTES = 9 * W0_TAP, W1_BYTES = 9 * W1_TAP;
+    static constexpr unsigned A0_BYTES = PX_IN * ROW0, A1_BYTES = PX_IN * ROW1, A_STAGE = A0_BYTES + A1_BYTES;
+    static constexpr unsigned PAD = 1024u;                               // the dx = -1 tap of the first row reads one row before the block
+    static constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = ((OFF_W1 + W1_BYTES + 1023u) & ~1023u) + (CIN == 96 ? 0u : PAD);
+    static constexpr unsigned OFF_BAR = (OFF_A + STAGES * A_STAGE + 1023u) & ~1023u;   // full[2], empty[2], wfull, tfull[4], tempty[4]
+    static constexpr unsigned OFF_TMEM = OFF_BAR + 13 * 8u;
+    static constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;  // GN epilogue: [2 passes][2 parity][12 warps][2 groups] f32
+    static constexpr unsigned OFF_CB = OFF_PART + 2 * 2 * 12 * 2 * 4u;   // [96] conv bias
+    static constexpr unsigned OFF_AB = OFF_CB + C * 4u;                  // [2 parity][2][96]: per-channel scale a, shift b of the board
+    static constexpr unsigned SMEM_BYTES = OFF_AB + 2 * 2 * C * 4u + 1024u;   // + slack to align the base to 1024 B
+};
 }  // namespace cv
 
 // What the fused GroupNorm epilogue needs (conv3x3_tc_kernel<true>); same meaning as msw_gn_act's arguments.
@@ -87,22 +99,16 @@ __device__ __forceinline__ void cv_tma_4d(unsigned dst, const CUtensorMap *map, 
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
-// K-major operand descriptors (sm_100 version bit, LBO unused = 1): 128-byte swizzle = rows 128 B apart, 8-row
-// groups 1024 B apart, layout type 2; 64-byte swizzle = rows 64 B apart, groups 512 B apart, layout type 4.
-__device__ __forceinline__ uint64_t cv_desc128(unsigned addr)
+// K-major operand descriptor (sm_100 version bit, LBO unused = 1, matrix base offset 0) for rows of ROW bytes:
+// 8-row groups ROW * 8 bytes apart (SBO); ROW = 128 / 64 / 32 <-> layout type SWIZZLE_128B (2) / 64B (4) / 32B (6).
+template <unsigned ROW>
+__device__ __forceinline__ uint64_t cv_desc(unsigned addr)
 {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t layout = ROW == 128 ? 2ull : ROW == 64 ? 4ull : 6ull;
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(ROW * 8u >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
-__device__ __forceinline__ uint64_t cv_desc64(unsigned addr)
-{
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
-}
-__device__ __forceinline__ void cv_mma(unsigned d_tmem, uint64_t a, uint64_t b, unsigned idesc, unsigned accumulate)
-{
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
-                 :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same with the disable-output-lane mask: bit i of word w set = row 32w + i of D is not written
+// D[tmem] (+)= A[smem] . B[smem]^T, issued by one thread; bit i of mask word w set = row 32w + i of D is not
+// written (disable-output-lane)
 __device__ __forceinline__ void cv_mma_masked(unsigned d_tmem, uint64_t a, uint64_t b, unsigned idesc, unsigned accumulate,
                                               unsigned mask)
 {
@@ -141,13 +147,17 @@ __device__ __forceinline__ float cv_warp_sum(float v)          // fixed shuffle 
 // GN = false: out = conv(x) (fp16).  GN = true: out = relu(GroupNorm(conv(x) + bias) [+ res]) [* Dropout2d], the
 // whole inter-convolution step of msw_gn_act fused into the epilogue (6 groups of 16 channels; statistics over
 // the board = the CTA's two consecutive tiles, whose fp16-rounded conv outputs wait in registers).
-template <bool GN>
+template <bool GN, int CIN>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                   __half *__restrict__ out, long long boards, int dbg, const __grid_constant__ ConvGnParams gp)
 {
     using namespace cv;
+    using K = Cfg<CIN>;
+    constexpr unsigned OFF_W0 = K::OFF_W0, OFF_W1 = K::OFF_W1, OFF_A = K::OFF_A, OFF_BAR = K::OFF_BAR, OFF_TMEM = K::OFF_TMEM,
+                       OFF_PART = K::OFF_PART, OFF_CB = K::OFF_CB, OFF_AB = K::OFF_AB, W0_TAP = K::W0_TAP, W1_TAP = K::W1_TAP,
+                       A0_BYTES = K::A0_BYTES, A_STAGE = K::A_STAGE;
     extern __shared__ unsigned char smem_dyn[];
     const unsigned base = (cv_smem(smem_dyn) + 1023u) & ~1023u;
     unsigned char *gen = smem_dyn + (base - cv_smem(smem_dyn));
@@ -178,10 +188,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
     if (warp == 0 && lane == 0) {
         // ---- TMA producer: the nine weight taps once, then one [10 rows x 16 px x 96 ch] block per tile
-        cv_bar_expect(wfull, W0_BYTES + W1_BYTES);
+        cv_bar_expect(wfull, K::W0_BYTES + K::W1_BYTES);
         for (int t = 0; t < 9; ++t) {
             cv_tma_2d(base + OFF_W0 + t * W0_TAP, &map_w0, 0, t * C, wfull);
-            cv_tma_2d(base + OFF_W1 + t * W1_TAP, &map_w1, 64, t * C, wfull);
+            if (K::KS1) cv_tma_2d(base + OFF_W1 + t * W1_TAP, &map_w1, K::BOX0, t * C, wfull);
         }
         // a CTA takes whole boards: tiles 2*board, 2*board + 1 back to back (the GN epilogue needs both)
         for (unsigned it = 0;; ++it) {
@@ -192,7 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             cv_bar_wait(empty(s), ph ^ 1u);
             cv_bar_expect(full(s), A_STAGE);
             cv_tma_4d(base + OFF_A + s * A_STAGE, &map_a0, 0, 0, y0 - 1, n, full(s));
-            cv_tma_4d(base + OFF_A + s * A_STAGE + A0_BYTES, &map_a1, 64, 0, y0 - 1, n, full(s));
+            if (K::KS1) cv_tma_4d(base + OFF_A + s * A_STAGE + A0_BYTES, &map_a1, K::BOX0, 0, y0 - 1, n, full(s));
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer.  idesc: D = F32, A = B = F16, K-major, M = 128, N = 96.
@@ -214,16 +224,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     const int tap = dy * 3 + dxi;
                     // rows of D whose horizontal neighbour is off the board: x = 0 for dx = -1, x = 15 for dx = +1
                     const unsigned mask = dxi == 0 ? 0x00010001u : dxi == 2 ? 0x80008000u : 0u;
-                    const unsigned sa0 = a0 + (unsigned)((dy * HW_W + dxi - 1) * 128), sa1 = a1 + (unsigned)((dy * HW_W + dxi - 1) * 64);
+                    const unsigned sa0 = a0 + (unsigned)((dy * HW_W + dxi - 1) * (int)K::ROW0);
+                    const unsigned sa1 = a1 + (unsigned)((dy * HW_W + dxi - 1) * (int)K::ROW1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {                            // channels 0..63: four 16-channel steps
-                        cv_mma_masked(d, cv_desc128(sa0) + 2u * k, cv_desc128(base + OFF_W0 + tap * W0_TAP) + 2u * k, idesc,
+                    for (int k = 0; k < K::KS0; ++k) {                       // first channel block, 16 channels (32 bytes) per step
+                        cv_mma_masked(d, cv_desc<K::ROW0>(sa0) + 2u * k, cv_desc<K::ROW0>(base + OFF_W0 + tap * W0_TAP) + 2u * k, idesc,
                                       accumulate, mask);
                         accumulate = 1u;
                     }
+                    if constexpr (K::KS1 > 0) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)                              // channels 64..95
-                        cv_mma_masked(d, cv_desc64(sa1) + 2u * k, cv_desc64(base + OFF_W1 + tap * W1_TAP) + 2u * k, idesc, 1u, mask);
+                        for (int k = 0; k < K::KS1; ++k)                     // second channel block
+                            cv_mma_masked(d, cv_desc<K::ROW1>(sa1) + 2u * k, cv_desc<K::ROW1>(base + OFF_W1 + tap * W1_TAP) + 2u * k,
+                                          idesc, 1u, mask);
+                    }
                 }
             cv_commit(empty(s));             // the smem stage is free once these MMAs have read it
             cv_commit(tfull(acc));           // ... and the accumulator is complete
@@ -435,82 +449,97 @@ static CvEncodeFn cv_encode_fn()
 
 }  // namespace msw
 
-// Shared host side of msw_conv3x3 / msw_conv3x3_gn: argument checks, the four tensor maps, the launch.
-static int conv_launch(const char *who, const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
-                       int32_t C, const msw::ConvGnParams *gn, void *stream)
+template <bool GN, int CIN>
+static int conv_launch_t(const CUtensorMap &ma0, const CUtensorMap &ma1, const CUtensorMap &mw0, const CUtensorMap &mw1, void *y16,
+                         int64_t n, int dbg, const msw::ConvGnParams &gp, cudaStream_t stream)
 {
     using namespace msw;
-    if (!x16 || !w_taps16 || !y16) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
-    if (H != 16 || W != 16 || C != cv::C)
-        return fail(MSW_ERR_BAD_SHAPE, "%s: only 16x16 boards with 96 channels (got %dx%d, C=%d)", who, H, W, C);
-    if (n < 0 || n > 0x3fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "%s: n=%lld", who, (long long)n);
-    if ((((uintptr_t)x16 | (uintptr_t)w_taps16 | (uintptr_t)y16) & 31u) != 0)
-        return fail(MSW_ERR_ALIGN, "%s: tensors must be 32-byte aligned", who);
-    if (n == 0) return MSW_OK;
-    if (!cv_encode_fn()) return fail(MSW_ERR_ARG, "%s: cuTensorMapEncodeTiled is not available", who);
-    CUtensorMap ma0, ma1, mw0, mw1;
-    {
-        // activation [n][16][16][96] fp16: dims innermost first
-        const cuuint64_t dims[4] = {(cuuint64_t)C, 16, 16, (cuuint64_t)n};
-        const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 16, (cuuint64_t)C * 2 * 256};
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const cuuint32_t box0[4] = {64, 16, cv::ROWS_IN, 1}, box1[4] = {32, 16, cv::ROWS_IN, 1};
-        const CUresult r0 = cv_encode_fn()(&ma0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x16), dims, strides,
-                                           box0, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        const CUresult r1 = cv_encode_fn()(&ma1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x16), dims, strides,
-                                           box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS)
-            return fail(MSW_ERR_ARG, "%s: activation tensor map failed (%d, %d)", who, (int)r0, (int)r1);
-    }
-    {
-        // weights [9 taps * 96 co][96 ci] fp16
-        const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
-        const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-        const cuuint32_t estr[2] = {1, 1};
-        const cuuint32_t box0[2] = {64, (cuuint32_t)C}, box1[2] = {32, (cuuint32_t)C};
-        const CUresult r0 = cv_encode_fn()(&mw0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_taps16), dims, strides,
-                                           box0, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        const CUresult r1 = cv_encode_fn()(&mw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_taps16), dims, strides,
-                                           box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r0 != CUDA_SUCCESS || r1 != CUDA_SUCCESS)
-            return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
-    }
+    using K = cv::Cfg<CIN>;
     static thread_local bool configured = false;
     if (!configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv::SMEM_BYTES));
-        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv::SMEM_BYTES));
+        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<GN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
         configured = true;
     }
     int dev = 0, sms = 0;
     MSW_CUDA_TRY(cudaGetDevice(&dev));
     MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long grid = n < sms ? n : sms;                       // persistent: whole boards per CTA
-    const char *e = getenv("MSW_CONV_DBG");
-    ConvGnParams none = {};
-    if (gn)
-        conv3x3_tc_kernel<true><<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(
-            ma0, ma1, mw0, mw1, (__half *)y16, (long long)n, 0, *gn);
-    else
-        conv3x3_tc_kernel<false><<<(unsigned)grid, cv::THREADS, cv::SMEM_BYTES, (cudaStream_t)stream>>>(
-            ma0, ma1, mw0, mw1, (__half *)y16, (long long)n, e ? atoi(e) : 0, none);
+    conv3x3_tc_kernel<GN, CIN><<<(unsigned)grid, cv::THREADS, K::SMEM_BYTES, stream>>>(ma0, ma1, mw0, mw1, (__half *)y16,
+                                                                                       (long long)n, dbg, gp);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
 }
 
-extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
-                           int32_t C, void *stream)
+// Shared host side of msw_conv3x3 / msw_conv3x3_gn: argument checks, the four tensor maps, the launch.
+static int conv_launch(const char *who, const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
+                       int32_t Cin, int32_t C, const msw::ConvGnParams *gn, void *stream)
 {
-    return conv_launch("msw_conv3x3", x16, w_taps16, y16, n, H, W, C, nullptr, stream);
+    using namespace msw;
+    if (!x16 || !w_taps16 || !y16) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
+    if (H != 16 || W != 16 || C != cv::C || (Cin != 96 && Cin != 16))
+        return fail(MSW_ERR_BAD_SHAPE, "%s: only 16x16 boards, 96 output and 96 or 16 input channels (got %dx%d, %d -> %d)", who, H,
+                    W, Cin, C);
+    if (n < 0 || n > 0x3fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "%s: n=%lld", who, (long long)n);
+    if ((((uintptr_t)x16 | (uintptr_t)w_taps16 | (uintptr_t)y16) & 31u) != 0)
+        return fail(MSW_ERR_ALIGN, "%s: tensors must be 32-byte aligned", who);
+    if (n == 0) return MSW_OK;
+    if (!cv_encode_fn()) return fail(MSW_ERR_ARG, "%s: cuTensorMapEncodeTiled is not available", who);
+    // first channel block: 64 channels / 128-byte swizzle (Cin = 96) or all 16 channels / 32-byte swizzle (Cin = 16);
+    // second block (Cin = 96 only): 32 channels / 64-byte swizzle
+    const cuuint32_t b0 = Cin == 96 ? 64u : 16u;
+    const CUtensorMapSwizzle sw0 = Cin == 96 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUtensorMap ma0, ma1, mw0, mw1;
+    {
+        // activation [n][16][16][Cin] fp16: dims innermost first
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, 16, 16, (cuuint64_t)n};
+        const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * 16, (cuuint64_t)Cin * 2 * 256};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const cuuint32_t box0[4] = {b0, 16, cv::ROWS_IN, 1}, box1[4] = {32, 16, cv::ROWS_IN, 1};
+        const CUresult r0 = cv_encode_fn()(&ma0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x16), dims, strides,
+                                           box0, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw0,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult r1 = cv_encode_fn()(&ma1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(x16), dims, strides,
+                                           box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r0 != CUDA_SUCCESS || (Cin == 96 && r1 != CUDA_SUCCESS))
+            return fail(MSW_ERR_ARG, "%s: activation tensor map failed (%d, %d)", who, (int)r0, (int)r1);
+    }
+    {
+        // weights [9 taps * 96 co][Cin] fp16
+        const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)9 * C};
+        const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint32_t box0[2] = {b0, (cuuint32_t)C}, box1[2] = {32, (cuuint32_t)C};
+        const CUresult r0 = cv_encode_fn()(&mw0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_taps16), dims, strides,
+                                           box0, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw0,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult r1 = cv_encode_fn()(&mw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_taps16), dims, strides,
+                                           box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r0 != CUDA_SUCCESS || (Cin == 96 && r1 != CUDA_SUCCESS))
+            return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
+    }
+    const char *e = getenv("MSW_CONV_DBG");
+    const int dbg = (!gn && e) ? atoi(e) : 0;
+    const ConvGnParams none = {};
+    const ConvGnParams &gp = gn ? *gn : none;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 96) return gn ? conv_launch_t<true, 96>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
+                             : conv_launch_t<false, 96>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+    return gn ? conv_launch_t<true, 16>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
+              : conv_launch_t<false, 16>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+}
+
+extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
+                           int32_t Cin, int32_t C, void *stream)
+{
+    return conv_launch("msw_conv3x3", x16, w_taps16, y16, n, H, W, Cin, C, nullptr, stream);
 }
 
 extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
                               const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
-                              int32_t W, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed, uint64_t call_id,
-                              const uint32_t *epoch, void *stream)
+                              int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed,
+                              uint64_t call_id, const uint32_t *epoch, void *stream)
 {
     using namespace msw;
     if (!conv_bias || !gamma || !beta) return fail(MSW_ERR_NULL, "msw_conv3x3_gn: NULL pointer");
@@ -525,5 +554,5 @@ extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
     g.call_lo = (uint32_t)call_id; g.call_hi = (uint32_t)(call_id >> 32);
     g.epoch = epoch;
-    return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, C, &g, stream);
+    return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, Cin, C, &g, stream);
 }

@@ -463,6 +463,47 @@ __global__ void __launch_bounds__(256) gn_act_bwd_kernel(const GnBwdParams p)
 
 }  // namespace msw
 
+namespace msw {
+
+// fp32 NCHW observation planes -> fp16 NHWC with the channels padded to 16 (zeros): the stem convolution's input
+// in the layout the tensor cores want, in one pass instead of a cast kernel plus cuDNN's own padding kernels.
+__global__ void __launch_bounds__(256) pack_obs16_kernel(const float *__restrict__ obs, uint4 *__restrict__ out, long long n,
+                                                         int Cin, int HW)
+{
+    const long long total = n * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / HW;
+        const int px = (int)(i - b * HW);
+        const float *src = obs + (b * Cin) * HW + px;           // consecutive threads read consecutive pixels of a plane
+        __half2 h[8];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+            const float v0 = c < Cin ? __ldcs(src + (long long)c * HW) : 0.0f;
+            const float v1 = c + 1 < Cin ? __ldcs(src + (long long)(c + 1) * HW) : 0.0f;
+            h[c >> 1] = __floats2half2_rn(v0, v1);
+        }
+        out[2 * i] = *reinterpret_cast<const uint4 *>(&h[0]);
+        out[2 * i + 1] = *reinterpret_cast<const uint4 *>(&h[4]);
+    }
+}
+
+}  // namespace msw
+
+extern "C" int msw_pack_obs16(const float *obs, void *out16, int64_t n, int32_t Cin, int32_t HW, void *stream)
+{
+    using namespace msw;
+    if (!obs || !out16) return fail(MSW_ERR_NULL, "msw_pack_obs16: NULL pointer");
+    if (n < 0 || Cin < 1 || Cin > 16 || HW < 1) return fail(MSW_ERR_BAD_SHAPE, "msw_pack_obs16: n=%lld Cin=%d HW=%d", (long long)n, Cin, HW);
+    if (((uintptr_t)out16 & 15u) != 0) return fail(MSW_ERR_ALIGN, "msw_pack_obs16: output must be 16-byte aligned");
+    if (n == 0) return MSW_OK;
+    const long long total = n * HW;
+    const long long blocks = (total + 255) / 256;
+    pack_obs16_kernel<<<(unsigned)(blocks < 148LL * 16 ? blocks : 148LL * 16), 256, 0, (cudaStream_t)stream>>>(
+        obs, (uint4 *)out16, n, Cin, HW);
+    MSW_CUDA_TRY(cudaGetLastError());
+    return MSW_OK;
+}
+
 extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *res32, const float *gamma,
                           const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,

@@ -80,14 +80,15 @@ def conv3x3(x16: torch.Tensor, taps16: torch.Tensor) -> torch.Tensor:
     """msw_conv3x3: x16 fp16 [N,C,16,16] channels_last, taps16 from `conv3x3_taps` -> fp16 conv output
     (no bias), same shape / memory format."""
     L = _lib.load()
-    N, C, H, W = x16.shape
+    N, Cin, H, W = x16.shape
     if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("conv3x3: x must be fp16 channels_last")
-    if taps16.dtype != torch.float16 or tuple(taps16.shape) != (9, C, C) or not taps16.is_contiguous():
-        raise ValueError("conv3x3: taps must be contiguous fp16 [9, C, C]")
-    y = torch.empty_like(x16, memory_format=torch.channels_last)
+    if taps16.dtype != torch.float16 or taps16.dim() != 3 or taps16.shape[0] != 9 or taps16.shape[2] != Cin or not taps16.is_contiguous():
+        raise ValueError("conv3x3: taps must be contiguous fp16 [9, C_out, C_in]")
+    C = taps16.shape[1]
+    y = torch.empty((N, C, H, W), dtype=torch.float16, device=x16.device, memory_format=torch.channels_last)
     with torch.cuda.device(x16.device):
-        rc = L.msw_conv3x3(x16.data_ptr(), taps16.data_ptr(), y.data_ptr(), N, H, W, C,
+        rc = L.msw_conv3x3(x16.data_ptr(), taps16.data_ptr(), y.data_ptr(), N, H, W, Cin, C,
                            torch.cuda.current_stream(x16.device).cuda_stream)
     _lib.check(rc, "msw_conv3x3")
     return y
@@ -98,22 +99,23 @@ def conv3x3_gn(x16: torch.Tensor, taps16: torch.Tensor, norm: torch.nn.GroupNorm
                call_id: int = 0, epoch: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """msw_conv3x3_gn = `gn_act(conv3x3(x16, taps16), norm, conv_bias=..., ...)` in one launch."""
     L = _lib.load()
-    N, C, H, W = x16.shape
+    N, Cin, H, W = x16.shape
     if x16.dtype != torch.float16 or not x16.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("conv3x3_gn: x must be fp16 channels_last")
-    if taps16.dtype != torch.float16 or tuple(taps16.shape) != (9, C, C) or not taps16.is_contiguous():
-        raise ValueError("conv3x3_gn: taps must be contiguous fp16 [9, C, C]")
+    if taps16.dtype != torch.float16 or taps16.dim() != 3 or taps16.shape[0] != 9 or taps16.shape[2] != Cin or not taps16.is_contiguous():
+        raise ValueError("conv3x3_gn: taps must be contiguous fp16 [9, C_out, C_in]")
+    C = taps16.shape[1]
     if res32 is not None and (res32.dtype != torch.float32 or tuple(res32.shape) != (N, C, H, W)
                               or not res32.is_contiguous(memory_format=torch.channels_last)):
         raise ValueError("conv3x3_gn: residual must be fp32 channels_last of the same shape")
     dev = x16.device
-    y16 = torch.empty_like(x16, memory_format=torch.channels_last)
+    y16 = torch.empty((N, C, H, W), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
     y32 = (torch.empty((N, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
            if want32 else None)
     with torch.cuda.device(dev):
         rc = L.msw_conv3x3_gn(x16.data_ptr(), taps16.data_ptr(), conv_bias.data_ptr(),
                               None if res32 is None else res32.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(),
-                              y16.data_ptr(), None if y32 is None else y32.data_ptr(), N, H, W, C, norm.num_groups,
+                              y16.data_ptr(), None if y32 is None else y32.data_ptr(), N, H, W, Cin, C, norm.num_groups,
                               float(norm.eps), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
                               int(call_id) & 0xFFFFFFFFFFFFFFFF, None if epoch is None else epoch.data_ptr(),
                               torch.cuda.current_stream(dev).cuda_stream)
@@ -162,6 +164,13 @@ class FusedRolloutForward:
 
             dev = p0.weight.device
             self.stem = conv3(m.stem[0])
+            cin = m.stem[0].in_channels
+            # stem weight with the input channels padded to 16 (zeros): pairs with msw_pack_obs16, so cuDNN gets a
+            # tensor-core friendly input and runs neither its padding kernels nor a separate cast
+            self.stem16 = (torch.zeros((C, 16, 3, 3), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+                           if cin <= 16 else None)
+            self.stem_taps = (torch.zeros((9, C, 16), dtype=torch.float16, device=dev)
+                              if cin <= 16 and C == 96 and os.environ.get("MSW_CONV", "tc") != "cudnn" else None)
             self.blocks = [(conv3(b.conv1), conv3(b.conv2)) for b in m.residual_stack]
             # tap-major fp16 copies of the trunk weights for msw_conv3x3 (tcgen05; 16x16 boards, 96 channels)
             self.taps = ([(torch.empty((9, C, C), dtype=torch.float16, device=dev),
@@ -180,6 +189,10 @@ class FusedRolloutForward:
             dst[1].copy_(c.bias)
 
         put3(self.stem, m.stem[0])
+        if self.stem16 is not None:
+            self.stem16[:, :m.stem[0].in_channels].copy_(m.stem[0].weight)
+        if self.stem_taps is not None:
+            self.stem_taps[:, :, :m.stem[0].in_channels].copy_(m.stem[0].weight.permute(2, 3, 0, 1).reshape(9, C, -1))
         for (d1, d2), b in zip(self.blocks, m.residual_stack):
             put3(d1, b.conv1)
             put3(d2, b.conv2)
@@ -200,8 +213,22 @@ class FusedRolloutForward:
         m = self.model
         self.calls += 1
         cid = self.calls << 8
-        x = obs.to(dtype=torch.float16, memory_format=torch.channels_last)
-        a16, a32 = gn_act(F.conv2d(x, self.stem[0], None, padding=1), m.stem[1], conv_bias=self.stem[1], want32=True)
+        if self.stem16 is not None and obs.dtype == torch.float32 and obs.is_contiguous():
+            nb, cin, hh, ww = obs.shape
+            x = torch.empty((nb, 16, hh, ww), dtype=torch.float16, device=obs.device, memory_format=torch.channels_last)
+            with torch.cuda.device(obs.device):
+                _lib.check(_lib.load().msw_pack_obs16(obs.data_ptr(), x.data_ptr(), nb, cin, hh * ww,
+                                                      torch.cuda.current_stream(obs.device).cuda_stream), "msw_pack_obs16")
+            if (self.stem_taps is not None and (hh, ww) == (16, 16) and m.stem[1].num_groups == 6
+                    and os.environ.get("MSW_CONV_GN", "1") != "0"):
+                c0 = None                        # stem conv + GroupNorm + ReLU in one launch
+                a16, a32 = conv3x3_gn(x, self.stem_taps, m.stem[1], self.stem[1], want32=True)
+            else:
+                c0 = F.conv2d(x, self.stem16, None, padding=1)
+        else:
+            c0 = F.conv2d(obs.to(dtype=torch.float16, memory_format=torch.channels_last), self.stem[0], None, padding=1)
+        if c0 is not None:
+            a16, a32 = gn_act(c0, m.stem[1], conv_bias=self.stem[1], want32=True)
         last = len(self.blocks) - 1
         pooled = None
         own_conv = self.taps is not None and tuple(a16.shape[2:]) == (16, 16)

@@ -176,8 +176,8 @@ def test_cell_heads_match_torch(C, R):
         assert float((got.float() - want.float()).abs().max()) <= 4e-3 * (float(want.float().abs().max()) + 1.0)
 
 
-@pytest.mark.parametrize("n", [1, 5, 300])
-def test_conv3x3_matches_cudnn(n):
+@pytest.mark.parametrize("n,cin", [(1, 96), (5, 96), (300, 96), (3, 16), (301, 16)])
+def test_conv3x3_matches_cudnn(n, cin):
     """msw_conv3x3 (tcgen05 implicit GEMM, nine shifted taps) vs cuDNN's fp16 convolution of the same
     operands: both accumulate in fp32 and round once to fp16, so they differ by summation order only."""
     import torch
@@ -185,8 +185,8 @@ def test_conv3x3_matches_cudnn(n):
     from minesweeper_ppo_b200.fused_forward import conv3x3, conv3x3_taps
     g = torch.Generator(device="cuda").manual_seed(n)
     C = 96
-    x = torch.randn((n, C, 16, 16), device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
-    w = (torch.randn((C, C, 3, 3), device="cuda", generator=g) / (9 * C) ** 0.5).half()
+    x = torch.randn((n, cin, 16, 16), device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((C, cin, 3, 3), device="cuda", generator=g) / (9 * cin) ** 0.5).half()
     got = conv3x3(x, conv3x3_taps(w))
     again = conv3x3(x, conv3x3_taps(w))
     assert torch.equal(got, again)
@@ -198,8 +198,8 @@ def test_conv3x3_matches_cudnn(n):
     # every tap in isolation (one-hot weights) catches a transposed or mis-shifted tap exactly
     for ky in range(3):
         for kx in range(3):
-            w1 = torch.zeros((C, C, 3, 3), device="cuda", dtype=torch.float16)
-            w1[:, :, ky, kx] = torch.eye(C, device="cuda", dtype=torch.float16)
+            w1 = torch.zeros((C, cin, 3, 3), device="cuda", dtype=torch.float16)
+            w1[:, :, ky, kx] = torch.eye(C, cin, device="cuda", dtype=torch.float16)
             one = conv3x3(x, conv3x3_taps(w1))
             ref = F.conv2d(x, w1.contiguous(memory_format=torch.channels_last), None, padding=1)
             assert torch.equal(one, ref), (ky, kx)
