@@ -52,7 +52,7 @@ struct Cfg {
     static constexpr unsigned OFF_W0 = 0, OFF_W1 = OFF_W0 + W0_BYTES, OFF_A = ((OFF_W1 + W1_BYTES + 1023u) & ~1023u) + (CIN == 96 ? 0u : PAD);
     static constexpr unsigned OFF_BAR = (OFF_A + STAGES * A_STAGE + 1023u) & ~1023u;   // full[2], empty[2], wfull, tfull[4], tempty[4]
     static constexpr unsigned OFF_TMEM = OFF_BAR + 13 * 8u;
-    static constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;  // GN epilogue: [2 passes][2 parity][12 warps][2 groups] f32
+    static constexpr unsigned OFF_PART = (OFF_TMEM + 16u + 15u) & ~15u;  // GN epilogue: [2 parity][12 warps][2 groups][mean, M2] f32
     static constexpr unsigned OFF_CB = OFF_PART + 2 * 2 * 12 * 2 * 4u;   // [96] conv bias
     static constexpr unsigned OFF_AB = OFF_CB + C * 4u;                  // [2 parity][2][96]: per-channel scale a, shift b of the board
     static constexpr unsigned SMEM_BYTES = OFF_AB + 2 * 2 * C * 4u + 1024u;   // + slack to align the base to 1024 B
@@ -283,7 +283,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         } else {
         // ---- fused GroupNorm epilogue.  Thread = pixel, its 32 channels = groups 2*third and 2*third + 1.
         const int we = warp - 4, te = tid - 128;                        // epilogue warp 0..11 = third*4 + q, thread 0..383
-        float *s_part = reinterpret_cast<float *>(gen + OFF_PART);      // [pass][parity][warp][group]
+        float *s_part = reinterpret_cast<float *>(gen + OFF_PART);      // [parity][warp][group][mean, M2]
         float *s_cb = reinterpret_cast<float *>(gen + OFF_CB);          // conv bias
         float *s_ab = reinterpret_cast<float *>(gen + OFF_AB);          // [parity][a | b][channel]
         const int cbase = third * 32;
@@ -295,8 +295,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             const long long board = blockIdx.x + (long long)bi * gridDim.x;
             if (board >= boards) break;
             const unsigned par = bi & 1u;
+            // Dropout2d scale of channel `te` for this board (msw_gn_act's stream: Philox keyed by board and 8-channel
+            // chunk).  It does not depend on the data, so it is drawn here, off the path between the two barriers.
+            float sc = gp.drop_scale;
+            if (te < C && gp.drop_p > 0.0f) {
+                uint32_t w[4];
+                philox4x32_10(gp.k0, gp.k1 ^ 0x44524f50u, (uint32_t)board, (uint32_t)(board >> 32) ^ (uint32_t)(te >> 3), gp.call_lo,
+                              gp.call_hi + (gp.epoch ? *gp.epoch : 0u), w);
+                const int k = te & 7;
+                const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                if (u16 < thresh) sc = 0.0f;
+            }
             uint32_t h[2][16];                       // fp16-rounded conv output of both tiles (the reference's rounding point)
-            float gs0 = 0.0f, gs1 = 0.0f;            // sum of (x + bias) over the thread's two groups
+            // One-pass statistics of v = x + bias, shifted by a value of the warp's own data (no cancellation in
+            // S2 - S1^2/n): per thread S1 = sum (v - shift), S2 = sum (v - shift)^2 for its two groups.
+            float shift0 = 0.0f, shift1 = 0.0f, s1a = 0.0f, s2a = 0.0f, s1b = 0.0f, s2b = 0.0f;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const unsigned it = 2u * bi + half, acc = it % ACC, aph = (it / ACC) & 1u;
@@ -318,57 +331,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     const __half2 hh = __floats2half2_rn(__uint_as_float(src[(2 * jj) & 15]), __uint_as_float(src[(2 * jj + 1) & 15]));
                     h[half][jj] = *reinterpret_cast<const uint32_t *>(&hh);
                     const float2 f = __half22float2(hh), cb = cb2[jj];
-                    if (jj < 8) gs0 += (f.x + cb.x) + (f.y + cb.y); else gs1 += (f.x + cb.x) + (f.y + cb.y);
+                    const float v0 = f.x + cb.x, v1 = f.y + cb.y;
+                    if (half == 0 && jj == 0) shift0 = __shfl_sync(0xffffffffu, v0, 0);
+                    if (half == 0 && jj == 8) shift1 = __shfl_sync(0xffffffffu, v0, 0);
+                    if (jj < 8) {
+                        const float d0 = v0 - shift0, d1 = v1 - shift0;
+                        s1a += d0 + d1;
+                        s2a = fmaf(d0, d0, fmaf(d1, d1, s2a));
+                    } else {
+                        const float d0 = v0 - shift1, d1 = v1 - shift1;
+                        s1b += d0 + d1;
+                        s2b = fmaf(d0, d0, fmaf(d1, d1, s2b));
+                    }
                 }
             }
-            // ---- statistics of the board: two passes over the registers (mean, then squared deviations)
-            gs0 = cv_warp_sum(gs0);
-            gs1 = cv_warp_sum(gs1);
-            if (lane == 0) { s_part[(0 * 2 + par) * 24 + we * 2 + 0] = gs0; s_part[(0 * 2 + par) * 24 + we * 2 + 1] = gs1; }
-            asm volatile("bar.sync 1, 384;" ::: "memory");
-            float mean[2];
-#pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-                float t = 0.0f;
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) t += s_part[(0 * 2 + par) * 24 + (third * 4 + qq) * 2 + g2];
-                mean[g2] = t * (1.0f / 4096.0f);
+            // the warp's (mean, M2) over its 1,024 values per group; the board's statistics are merged from the four
+            // row-owning warps of a channel third in a fixed order (Chan et al.)
+            s1a = cv_warp_sum(s1a); s2a = cv_warp_sum(s2a);
+            s1b = cv_warp_sum(s1b); s2b = cv_warp_sum(s2b);
+            if (lane == 0) {
+                float *dst = s_part + (par * 12 + we) * 4;
+                dst[0] = shift0 + s1a * (1.0f / 1024.0f); dst[1] = s2a - s1a * s1a * (1.0f / 1024.0f);
+                dst[2] = shift1 + s1b * (1.0f / 1024.0f); dst[3] = s2b - s1b * s1b * (1.0f / 1024.0f);
             }
-            float q0 = 0.0f, q1 = 0.0f;
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h[half][jj])), cb = cb2[jj];
-                    const float m = jj < 8 ? mean[0] : mean[1];
-                    const float d0 = (f.x + cb.x) - m, d1 = (f.y + cb.y) - m;
-                    if (jj < 8) q0 = fmaf(d0, d0, fmaf(d1, d1, q0)); else q1 = fmaf(d0, d0, fmaf(d1, d1, q1));
-                }
-            q0 = cv_warp_sum(q0);
-            q1 = cv_warp_sum(q1);
-            if (lane == 0) { s_part[(1 * 2 + par) * 24 + we * 2 + 0] = q0; s_part[(1 * 2 + par) * 24 + we * 2 + 1] = q1; }
             asm volatile("bar.sync 1, 384;" ::: "memory");
             if (te < C) {
-                // one thread per channel folds statistics, affine, conv bias and the Dropout2d scale (msw_gn_act's
-                // stream: Philox keyed by board and 8-channel chunk) into y = a*x + b
+                // one thread per channel folds statistics, affine, conv bias and the Dropout2d scale into y = a*x + b
                 const int c = te, gsel = (c >> 4) & 1, w4 = (c >> 5) * 4;
-                float t0 = 0.0f, t1 = 0.0f;
+                float na = 0.0f, mg = 0.0f, m2 = 0.0f;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    t0 += s_part[(0 * 2 + par) * 24 + (w4 + qq) * 2 + gsel];
-                    t1 += s_part[(1 * 2 + par) * 24 + (w4 + qq) * 2 + gsel];
+                    const float *src = s_part + (par * 12 + w4 + qq) * 4 + 2 * gsel;
+                    const float nn = na + 1024.0f, delta = src[0] - mg, w = 1024.0f / nn;
+                    mg = fmaf(delta, w, mg);
+                    m2 += src[1] + delta * delta * (na * w);
+                    na = nn;
                 }
-                const float mg = t0 * (1.0f / 4096.0f);
-                const float rg = rsqrtf(t1 * (1.0f / 4096.0f) + gp.eps);       // biased variance, eps as torch
-                float sc = gp.drop_scale;
-                if (gp.drop_p > 0.0f) {
-                    uint32_t w[4];
-                    philox4x32_10(gp.k0, gp.k1 ^ 0x44524f50u, (uint32_t)board, (uint32_t)(board >> 32) ^ (uint32_t)(c >> 3), gp.call_lo,
-                                  gp.call_hi + (gp.epoch ? *gp.epoch : 0u), w);
-                    const int k = c & 7;
-                    const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-                    if (u16 < thresh) sc = 0.0f;
-                }
+                const float rg = rsqrtf(m2 * (1.0f / 4096.0f) + gp.eps);       // biased variance, eps as torch
                 const float a = gp.gamma[c] * rg;
                 s_ab[(par * 2 + 0) * C + c] = a * sc;
                 s_ab[(par * 2 + 1) * C + c] = fmaf(s_cb[c] - mg, a, gp.beta[c]) * sc;
