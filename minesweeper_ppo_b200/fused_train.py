@@ -10,12 +10,14 @@ fp32 tensors (the fp16 casts are part of the graph), so AdamW / GradScaler / cli
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .fused_forward import conv3x3, conv3x3_taps
 from .policy import CNNResidualPolicy
 
 _CL = torch.channels_last
@@ -88,7 +90,34 @@ def supports(model) -> bool:
     return C % 8 == 0 and (C // G) % 8 == 0
 
 
+class Conv3x3Tc(torch.autograd.Function):
+    """3x3 trunk convolution on the tcgen05 kernel (msw_conv3x3) with its data gradient on the same kernel:
+    dL/dx is the convolution of dL/dy with the taps flipped in space and transposed in the channels.  The weight
+    gradient stays cuDNN's wgrad (fp16 operands, as the autocast path computes it)."""
+
+    @staticmethod
+    def forward(ctx, x16, weight):
+        ctx.save_for_backward(x16, weight)
+        return conv3x3(x16, conv3x3_taps(weight))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x16, weight = ctx.saved_tensors
+        gy = gy.to(torch.float16).contiguous(memory_format=_CL)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            co, ci = weight.shape[0], weight.shape[1]
+            taps_t = weight.detach().flip(2, 3).permute(2, 3, 1, 0).to(torch.float16).reshape(9, ci, co).contiguous()
+            gx = conv3x3(gy, taps_t)
+        if ctx.needs_input_grad[1]:
+            gw = torch.nn.grad.conv2d_weight(x16, weight.shape, gy, padding=1).to(weight.dtype)
+        return gx, gw
+
+
 def _conv3(x16: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    if (conv.in_channels == 96 and conv.out_channels == 96 and tuple(x16.shape[2:]) == (16, 16)
+            and os.environ.get("MSW_CONV", "tc") != "cudnn"):
+        return Conv3x3Tc.apply(x16, conv.weight)
     w16 = conv.weight.to(torch.float16).contiguous(memory_format=_CL)      # differentiable cast
     return F.conv2d(x16, w16, None, padding=1)
 

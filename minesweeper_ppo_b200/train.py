@@ -267,7 +267,8 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
         "ms_rollout_gae": 1e3 * t_roll / n_timed, "ms_ppo_epochs": 1e3 * t_upd / n_timed,
         "optimizer_steps_per_update": cfg.ppo_epochs * cfg.mini_batches,
         "grad_allreduce_bytes": grads.numel * 4, "replica_param_checksum_spread": spread,
-        "training_forward": "fused GroupNorm fwd+bwd (msw_gn_act / msw_gn_act_bwd)" if train_fwd else "eager module",
+        "training_forward": ("fused GroupNorm fwd+bwd (msw_gn_act / msw_gn_act_bwd), trunk conv fwd + dgrad on tcgen05 (msw_conv3x3)"
+                             if train_fwd else "eager module"),
     }
     if world > 1:
         dist.destroy_process_group()
