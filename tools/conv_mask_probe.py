@@ -1,5 +1,6 @@
-"""Development: does the single-accumulator conv variant (MSW_CONV_DBG=4: shifted A descriptors with a matrix
-base offset + disable-output-lane masks) reproduce each tap exactly?  Run with MSW_CONV_DBG=4."""
+"""Development: per-tap exactness of msw_conv3x3 (one accumulator, row-shifted A descriptors, disable-output-lane
+masks), separately for the 128-byte- and the 64-byte-swizzled channel block.  profiles/r01j_conv_descriptor_probe.txt
+holds its output for the two descriptor variants tried in round 1."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
