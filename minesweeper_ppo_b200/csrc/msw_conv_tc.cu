@@ -1,6 +1,7 @@
-// msw_conv_tc.cu -- 3x3 "same" convolution of the residual trunk (96 -> 96 channels on 16x16 boards,
-// fp16 NHWC in, fp32 accumulate, fp16 NHWC out, no bias: the bias is folded into msw_gn_act) on the
-// 5th-generation tensor cores.
+// msw_conv_tc.cu -- 3x3 "same" convolution of the policy trunk (96 -> 96 channels on 16x16 boards, and the stem's
+// 16 -> 96; fp16 NHWC in, fp32 accumulate, fp16 NHWC out) on the 5th-generation tensor cores, plain
+// (conv3x3_tc_kernel<false>: no bias, it is folded into msw_gn_act) or with GroupNorm / ReLU / Dropout2d /
+// residual add fused into the epilogue (conv3x3_tc_kernel<true>).
 //
 // out[y][x][co] = sum_{dy,dx,ci} in[y+dy][x+dx][ci] * w[co][ci][dy][dx] is computed as nine shifted GEMMs
 // per 128-pixel tile (8 image rows of one board) that all accumulate into ONE TMEM accumulator.  The tile's
