@@ -11,7 +11,6 @@ fp32 tensors (the fp16 casts are part of the graph), so AdamW / GradScaler / cli
 from __future__ import annotations
 
 import os
-from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -26,7 +26,6 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import fused_train as fused_train_mod
-from .buffers import RolloutBuffer
 from .env import EnvConfig, VecMinesweeper
 from .policy import build_model
 from .rollout import RolloutCollector
