@@ -1056,7 +1056,7 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     const int mode = host_mode();
 
     struct Copy { void *dst; const void *src; size_t bytes; };
-    Copy copies[8];
+    Copy copies[8] = {};
     int nc = 0;
     // Queue a device->host copy; a copy that continues the previous one on both sides is merged into it
     // (the Python mirror lays reward|done|... out back to back, so the scalars travel as one DMA).

@@ -22,7 +22,6 @@
 
 namespace msw {
 
-constexpr int SAMPLER_MAX_PER_LANE = MSW_MAX_CELLS / 32;   // A <= 1024
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
