@@ -57,6 +57,35 @@ def env_cfg(mod):
     return mod.EnvConfig(H=H, W=W, mine_count=MINES, guarantee_safe_neighborhood=True, step_penalty=1e-4)
 
 
+def bench_config(world: int) -> dict:
+    """The workload both arms run (identical dict in the CUDA arm and in --impl reference)."""
+    return {
+        "workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_per_gpu": ENVS_PER_GPU,
+        "envs_total": ENVS_PER_GPU * world,
+        "actions": ("uniform random valid cell" if VALID_ONLY else "uniform random cell (series B, no-op clicks included)")
+                   + " per env per step",
+        "auto_reset": True, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
+        "l2": f"each step writes {BYTES_PER_STEP * ENVS_PER_GPU / 1e6:.0f} MB of obs/mask (>> 126 MB L2), no explicit flush",
+        "parallelism": f"env shards, {world} rank(s), no data-path collective",
+    }
+
+
+def numba_reference_baseline(quick: bool = False):
+    """the REAL reference env (Python + numba, baseline/_ref) timed on this
+    box's host cores by tools/numba_reference_bench.py in a fresh interpreter."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "numba_reference_bench.py")] + (["--quick"] if quick else [])
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": f"numba_reference_bench rc={r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": repr(e)}
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
@@ -184,19 +213,61 @@ def run_reference_arm(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_sampled": n,
-                   "actions": "uniform random valid cell"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "envs_sampled": n, "reference_numba": numba_reference_baseline()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python (+1 numba kernel) and cannot travel to the GPU box; this arm is the "
-                "C restatement of its algorithm (oracle/), multi-threaded over envs -- a much FASTER baseline than "
-                "the reference itself (about 2e4 env-steps/s on one core, BASELINE.md section 2)",
+        "note": "value = the C restatement of the reference's algorithm (oracle/msw_oracle.c) on all host threads -- "
+                "the FASTEST CPU implementation available, so the GPU/CPU ratio is conservative; the unmodified "
+                "Python+numba reference timed on the same cores is cpu_baseline.reference_numba (one core as "
+                "shipped, and a P-process fan-out)",
     }
     emit_json(line)
 
 
 # ----------------------------------------------------------------------------- CUDA arm
+def time_env_steps(torch, m, dev, rank, world, barrier, board, n_envs, K, Wm, ring, valid_only=True, keep_actions=0):
+    """The device-timed leg for one board/env-count: W untimed + K timed fused step launches (built-in
+    synthetic policy), CUDA events around the K launches only; then a separate replay of up to 64 more
+    launches with an event pair around EACH launch (per-launch kernel time for the roofline) -- no event
+    pair sits inside the timed region."""
+    h, w, mines = board
+    cfg = m.EnvConfig(H=h, W=w, mine_count=mines, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    vec = m.VecMinesweeper(n_envs, cfg, seed=0, api="torch", env_id_base=rank * n_envs)
+    slots = [m.StepOut(obs=torch.empty((n_envs, 10, h, w), dtype=torch.float32, device=dev),
+                       action_mask=torch.empty((n_envs, h * w), dtype=torch.bool, device=dev),
+                       rewards=torch.empty((n_envs,), dtype=torch.float32, device=dev),
+                       dones=torch.empty((n_envs,), dtype=torch.bool, device=dev)) for _ in range(ring)]
+    log = torch.empty((Wm + keep_actions + 1, n_envs), dtype=torch.int32, device=dev) if keep_actions else None
+    scratch = torch.empty((n_envs,), dtype=torch.int32, device=dev)
+    vec.reset(out=slots[0])
+    for t in range(Wm):
+        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=log[t] if keep_actions else scratch)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(torch, dev.index)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for t in range(K):
+        a = log[Wm + min(t, keep_actions)] if keep_actions else scratch
+        vec.step_random(Wm + t, valid_only=valid_only, out=slots[t % ring], actions_out=a)   # policy + step: one launch
+    ev1.record()
+    clocks = sampler.finish()          # sampled while the last launches are still executing
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    Kk = min(64, max(8, K))
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    for t in range(Kk):
+        kev[t][0].record()
+        vec.step_random(Wm + K + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
+        kev[t][1].record()
+    barrier()
+    ms_kernel = float(np.mean([x.elapsed_time(y) for x, y in kev]))
+    del vec, slots
+    return ms_total, ms_kernel, clocks, log
+
+
 def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -217,33 +288,24 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    vec = make_env()
-    slots = [m.StepOut(obs=torch.empty((N, 10, H, W), dtype=torch.float32, device=dev),
-                       action_mask=torch.empty((N, H * W), dtype=torch.bool, device=dev),
-                       rewards=torch.empty((N,), dtype=torch.float32, device=dev),
-                       dones=torch.empty((N,), dtype=torch.bool, device=dev)) for _ in range(ring)]
-    Ke = min(K, 400)                           # steps replayed by the e2e legs
-    actions_log = torch.empty((Wm + Ke + 1, N), dtype=torch.int32, device=dev)
-    vec.reset(out=slots[0])
-    for t in range(Wm):
-        vec.step_random(t, valid_only=VALID_ONLY, out=slots[t % ring], actions_out=actions_log[t])
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sampler = ClockSampler(torch, local_rank)
-    barrier()
-    sampler.start()
-    ev0.record()
-    for t in range(K):
-        a = actions_log[Wm + min(t, Ke)]       # first Ke action sets are kept for the e2e replay
-        kev[t][0].record()
-        vec.step_random(Wm + t, valid_only=VALID_ONLY, out=slots[t % ring], actions_out=a)   # policy + step: one launch
-        kev[t][1].record()
-    ev1.record()
-    clocks = sampler.finish()          # sampled while the last launches are still executing
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / K
+    def gather(x: float):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    Ke = min(K, 400)                           # steps replayed by the e2e legs
+    ms_total, ms_kernel, clocks, actions_log = time_env_steps(torch, m, dev, rank, world, barrier, (H, W, MINES), N, K, Wm,
+                                                              ring, VALID_ONLY, keep_actions=Ke)
     episodes = None
 
     # -- e2e: same workload through the host-buffer C-ABI call (msw_step_host): per step, this
@@ -251,6 +313,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     # memory (D2H); obs/mask land in device memory where the policy consumes them.
     acts_host = actions_log[: Wm + Ke].cpu().pin_memory()
     del actions_log
+    torch.cuda.empty_cache()
 
     def run_host(copy_obs: bool, steps: int):
         v = make_env()
@@ -269,7 +332,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
-        return max(e0.elapsed_time(e1) / 1e3, 0.0), wall, done_count
+        return max(e0.elapsed_time(e1) / 1e3, wall), wall, done_count
 
     if args.no_e2e:
         Kh = 1
@@ -279,20 +342,18 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         Kh = min(Ke, 12)
         e2e_full_s, _, _ = run_host(True, Kh)
 
-    def reduce_max(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     ms_total_max = reduce_max(ms_total)
     e2e_s_max = reduce_max(e2e_s)
     e2e_full_max = reduce_max(e2e_full_s)
-    ms_kernel_max = reduce_max(ms_kernel)
+    kernel_ms_ranks = gather(ms_kernel)
+    ms_kernel_max = max(kernel_ms_ranks)
+    del acts_host
+    torch.cuda.empty_cache()
 
     gae_info = None if args.no_gae else bench_gae(torch, m, dev)
     roll_info = None if args.no_rollout else bench_rollout(torch, m, dev, rank, world, reduce_max)
+    c4_info = None if (args.no_c4 or WORKLOAD != "C2") else bench_c4(torch, m, dev, rank, world, barrier, reduce_max, gather)
+    c5_info = None if args.no_train else bench_train_c5(torch, m, dev, rank, world)
 
     if rank != 0:
         return
@@ -301,24 +362,21 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     peak, peak_src = measured_peak_gbs()
     achieved = BYTES_PER_STEP * N / (ms_kernel_max / 1e3) / 1e9
     traffic = profiled_traffic() if (WORKLOAD == "C2" and N == 65536) else None
+    config = bench_config(world)
+    config["action_source"] = ("drawn inside the step launch (msw_step rand_mode; bit-identical to msw_random_actions); "
+                               f"obs/mask stream into a ring of {ring} rollout-buffer slots")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD, "board": f"{H}x{W}x{MINES}", "envs_per_gpu": N, "envs_total": total_envs,
-            "actions": ("uniform random valid cell" if VALID_ONLY else "uniform random cell (series B, no-op clicks included)")
-                       + " per env per step, drawn inside the step launch (msw_step rand_mode; identical to "
-                         "msw_random_actions)",
-            "auto_reset": True, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
-            "l2": f"each step writes {BYTES_PER_STEP * N / 1e6:.0f} MB of obs/mask into a ring of {ring} slots "
-                  "(>> 126 MB L2), no explicit flush",
-            "parallelism": f"env shards, {world} rank(s), no data-path collective",
-        },
+        "config": config,
         "roofline": {
             "bound": "hbm", "kernel": f"msw::env_kernel<MODE_STEP,{W},{H * W}>", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": BYTES_PER_STEP * N, "kernel_ms": ms_kernel_max,
+            "kernel_ms_per_rank": kernel_ms_ranks,
+            "kernel_ms_how": "mean over a separate replay of launches, one CUDA-event pair per launch, after the timed "
+                             "region (no event pairs inside it); max over ranks",
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),
         },
@@ -331,13 +389,15 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         },
         "e2e_host_obs": {
             "value": total_envs * Kh / e2e_full_max, "unit": UNIT, "steps": Kh,
-            "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": (40 * H * W + H * W + 5) * N,
+            "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": host_obs_d2h_bytes(m, N),
             "call": "same call with copy_obs=True: the full reference-shaped NumPy result (obs+mask+reward+done) "
-                    "copied to pinned host memory every step; PCIe-bound by construction",
+                    "in host memory every step",
         },
         "gpu_launches": K,
         "gae": gae_info,
         "rollout": roll_info,
+        "c4": c4_info,
+        "train_c5": c5_info,
         "clocks": clocks,
         "episodes_finished_in_e2e": episodes,
     }
@@ -350,10 +410,46 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         line["cpu_baseline"] = {
             "value": v_c, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_c} envs x {steps_c} steps of the same workload on the host ({total_c:.1f} s), "
-                      "oracle/msw_oracle.c (C restatement of env.py/env_numba.py; the Python reference itself runs "
-                      "~2e4 env-steps/s on one core, BASELINE.md section 2)",
+                      "oracle/msw_oracle.c (C restatement of env.py/env_numba.py) on all host threads",
+            "reference_numba": numba_reference_baseline(),
         }
     emit_json(line)
+
+
+def host_obs_d2h_bytes(m, n_envs: int) -> int:
+    """Bytes msw_step_host moves device->host per step when the caller wants obs+mask on the host."""
+    f = getattr(m.VecMinesweeper, "host_obs_d2h_bytes", None)
+    return int(f(H, W, n_envs)) if f else (40 * H * W + H * W + 5) * n_envs
+
+
+def bench_c4(torch, m, dev, rank, world, barrier, reduce_max, gather):
+    """BASELINE.json configs[3] (C4): Expert boards (H=16, W=30, 99 mines), 524,288 envs per GPU
+    (= 4,194,304 over 8 GPUs), env-only random valid actions; roofline at 19,689 B per env-step."""
+    h, w, mines, n = 16, 30, 99, 524288
+    K, Wm = 12, 3
+    bps = 41 * h * w + 9
+    ms_total, ms_kernel, _, _ = time_env_steps(torch, m, dev, rank, world, barrier, (h, w, mines), n, K, Wm, 2)
+    torch.cuda.empty_cache()
+    ms_max = reduce_max(ms_total)
+    kr = gather(ms_kernel)
+    peak, _ = measured_peak_gbs()
+    ach = bps * n / (max(kr) / 1e3) / 1e9
+    return {"workload": "C4", "board": f"{h}x{w}x{mines}", "envs_per_gpu": n, "envs_total": n * world, "steps": K,
+            "env_steps_per_s": n * world * K / (ms_max / 1e3), "ms_per_step": ms_max / K,
+            "algorithmic_bytes_per_env_step": bps, "kernel_ms": max(kr), "kernel_ms_per_rank": kr,
+            "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak,
+            "l2": f"each step writes {bps * n / 1e9:.1f} GB into a ring of 2 slots, no explicit flush"}
+
+
+def bench_train_c5(torch, m, dev, rank, world):
+    """BASELINE.json configs[4] (C5): the full PPO loop of the medium config (16x16x40, 96x5 residual CNN),
+    2,048 envs x 64 steps per GPU, env shards per GPU, ONE NCCL all-reduce of the flat gradient per
+    optimizer step; 1 warm-up + 2 timed updates."""
+    from minesweeper_ppo_b200 import train as T
+    r = T.train(os.path.join(ROOT, "configs", "medium_16x16x40.yaml"), updates=3, envs_per_gpu=2048, steps=64, seed=0,
+                log=lambda s: None, time_allreduce=True)
+    torch.cuda.empty_cache()
+    return r if rank == 0 else None
 
 
 def bench_gae(torch, m, dev):
@@ -475,7 +571,7 @@ def bench_rollout(torch, m, dev, rank, world, reduce_max):
     flops = 0.44e9 * N * (T + 1)                      # ~0.44 GFLOP / board / forward
     return {"workload": "C3", "frames_per_s": world * N * T / (ms / 1e3), "envs_per_gpu": N, "steps": T,
             "ms_rollout": ms_roll, "ms_gae": ms_gae,
-            "forward": "trunk 3x3 convs on tcgen05 (msw_conv3x3; the 10-channel stem conv stays cuDNN) + fused GroupNorm/ReLU/Dropout2d/residual kernel (msw_gn_act) + fused per-cell heads on tcgen05 (msw_cell_heads)",
+            "forward": "stem + trunk 3x3 convs on tcgen05 with GroupNorm / ReLU / Dropout2d / fp32 residual add fused into the epilogue (msw_conv3x3_gn, obs packed by msw_pack_obs16) + fused per-cell heads on tcgen05 (msw_cell_heads); no cuDNN on the path",
             "model": "cnn_residual 96x5 (950,947 params), random init, train mode (dropout on, as the reference)",
             "model_tflops_est": flops / (ms_roll / 1e3) / 1e12, "episodes_in_buffer": episodes,
             "stock_module_forward": {"frames_per_s": world * N * T / (s_ms / 1e3), "ms_rollout": s_roll,
@@ -528,6 +624,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value and roofline only")
     ap.add_argument("--no-gae", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     set_workload(args.workload, args.envs)

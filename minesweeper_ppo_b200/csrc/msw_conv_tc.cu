@@ -455,14 +455,8 @@ static int conv_launch_t(const CUtensorMap &ma0, const CUtensorMap &ma1, const C
 {
     using namespace msw;
     using K = cv::Cfg<CIN>;
-    static thread_local bool configured = false;
-    if (!configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<GN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
-        configured = true;
-    }
-    int dev = 0, sms = 0;
-    MSW_CUDA_TRY(cudaGetDevice(&dev));
-    MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MSW_SET_MAX_SMEM((conv3x3_tc_kernel<GN, CIN>), K::SMEM_BYTES);
+    const int sms = sm_count();
     const long long grid = n < sms ? n : sms;                       // persistent: whole boards per CTA
     conv3x3_tc_kernel<GN, CIN><<<(unsigned)grid, cv::THREADS, K::SMEM_BYTES, stream>>>(ma0, ma1, mw0, mw1, (__half *)y16,
                                                                                        (long long)n, dbg, gp);
@@ -519,8 +513,7 @@ static int conv_launch(const char *who, const void *x16, const void *w_taps16, v
         if (r0 != CUDA_SUCCESS || (Cin == 96 && r1 != CUDA_SUCCESS))
             return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
     }
-    const char *e = getenv("MSW_CONV_DBG");
-    const int dbg = (!gn && e) ? atoi(e) : 0;
+    const int dbg = 0;
     const ConvGnParams none = {};
     const ConvGnParams &gp = gn ? *gn : none;
     cudaStream_t st = (cudaStream_t)stream;

@@ -19,9 +19,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#ifndef MSW_HOST_MODE_DEFAULT
-#define MSW_HOST_MODE_DEFAULT 0
-#endif
 
 namespace msw {
 
@@ -873,82 +870,54 @@ static int set_encode_out(EnvParams &p, const msw_encode_out *out, bool require)
 // Launch shape.  Stores reach full HBM write bandwidth only when CTAs are handed out
 // dynamically (profiles/r01_store_probe2.txt: a static one-wave grid tops out near 6.0 TB/s,
 // the same stores from many short CTAs reach 6.9-7.0 TB/s), so the grid is sized from
-// boards-per-warp rather than from the SM count.  Development knobs (environment, read once):
-//   MSW_BLOCK        threads per CTA (32..256; default 32: one warp per CTA, so a slow board --
-//                    a deep flood fill, a board draw -- never holds other warps' slots)
-//   MSW_BPW          boards per warp (default 3, with the next board's state prefetched);
-//                    0 = use MSW_CTAS_PER_SM
-// Sweep: profiles/r01_sweep_launch_shape.txt.
-//   MSW_CTAS_PER_SM  cap the grid at that many CTAs per SM (warps stride over boards)
-static inline int env_int(const char *name, int dflt)
-{
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
+// boards-per-warp rather than from the SM count:
+//   CTA = one warp (a slow board -- a deep flood fill, a board draw -- never holds other warps' slots),
+//   3 boards per warp with the next board's state prefetched (80 registers).
+// Sweeps: profiles/r01_sweep_launch_shape.txt, profiles/r01_sweep_*.txt.  The product library has ONE
+// shape; building with -DMSW_DEV_KNOBS (tools/ only) lets MSW_BLOCK / MSW_BPW override it for sweeps.
+struct LaunchShape { int block, bpw; };
 
-struct LaunchShape { int block, bpw, cap; };
-
-static inline const LaunchShape &launch_shape_cfg()
+static inline LaunchShape launch_shape_cfg()
 {
+#ifdef MSW_DEV_KNOBS
     static const LaunchShape c = [] {                 // initialised once, thread-safe (C++11 static init)
+        auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
         LaunchShape v;
         int blk = env_int("MSW_BLOCK", 32);
         if (blk < 32) blk = 32;
         if (blk > 256) blk = 256;
         v.block = blk & ~31;
         v.bpw = env_int("MSW_BPW", 3);
-        v.cap = env_int("MSW_CTAS_PER_SM", 8);
-        if (v.bpw < 0) v.bpw = 0;
-        if (v.cap < 0) v.cap = 0;
+        if (v.bpw < 1) v.bpw = 1;
         return v;
     }();
     return c;
+#else
+    return LaunchShape{32, 3};
+#endif
 }
 
 static inline int grid_for(long long n, int *block_out)
 {
-    const LaunchShape &c = launch_shape_cfg();
+    const LaunchShape c = launch_shape_cfg();
     const int wpc = c.block / 32;
     *block_out = c.block;
-    long long blocks;
-    if (c.bpw > 0) {
-        const long long warps = (n + c.bpw - 1) / c.bpw;
-        blocks = (warps + wpc - 1) / wpc;
-    } else {
-        blocks = (n + wpc - 1) / wpc;
-        if (c.cap > 0) {
-            const long long cap = (long long)sm_count() * c.cap;
-            if (blocks > cap) blocks = cap;
-        }
-    }
+    const long long warps = (n + c.bpw - 1) / c.bpw;
+    long long blocks = (warps + wpc - 1) / wpc;
     if (blocks < 1) blocks = 1;
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
     return (int)blocks;
 }
 
-// MSW_VARIANT (development knob, see profiles/r01_sweep_*.txt): 2 (default) = next-board prefetch,
-// 80 registers; 0 = no prefetch, 64 registers.  (1 = prefetch at 64 registers and 3 = no prefetch at
-// 48 registers were measured slower and dropped.)
-static inline int variant()
-{
-    static const int cached = [] {
-        const char *e = getenv("MSW_VARIANT");
-        return (e && atoi(e) == 0) ? 0 : 2;
-    }();
-    return cached;
-}
-
+// Step launches use the next-board-prefetch instantiation (80 registers); reset / encode the plain one.
+// (Prefetch at 64 registers, no prefetch at 64 and at 48 registers were measured slower and dropped.)
 template <int MODE, int CW, int CHW>
 static void launch_shape(const EnvParams &p, int grid, int block, cudaStream_t s)
 {
-    if (MODE != MODE_STEP) {
+    if (MODE != MODE_STEP)
         env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p);
-        return;
-    }
-    if (variant() == 2)
-        env_kernel<MODE, CW, CHW, true, 3><<<grid, block, 0, s>>>(p);
     else
-        env_kernel<MODE, CW, CHW, false, 4><<<grid, block, 0, s>>>(p);
+        env_kernel<MODE, CW, CHW, true, 3><<<grid, block, 0, s>>>(p);
 }
 
 template <int MODE>
@@ -1022,28 +991,6 @@ extern "C" int msw_step(const msw_env_desc *desc, const msw_state *st, const msw
     return launch_env<MODE_STEP>(p, (cudaStream_t)stream);
 }
 
-// Transfer plan of msw_step_host.  bit 0: the kernel reads the actions straight from the pinned
-// host buffer (no H2D copy node); bit 1: the per-env scalar outputs are written by the kernel
-// straight into the pinned host buffers (no D2H copy nodes).  MSW_HOST_MODE overrides the default
-// for measurements (tools/e2e_probe.sh).
-static int host_mode()
-{
-    static const int mode = [] {
-        const char *e = getenv("MSW_HOST_MODE");
-        return e ? atoi(e) : MSW_HOST_MODE_DEFAULT;
-    }();
-    return mode;
-}
-
-static int mapped_ptr(void **dev, const void *host, const char *what)
-{
-    if (cudaHostGetDevicePointer(dev, const_cast<void *>(host), 0) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(MSW_ERR_ARG, what);
-    }
-    return MSW_OK;
-}
-
 extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, const msw_step_io *io,
                              const int32_t *h_actions32, const msw_host_out *h, int64_t n, void *stream)
 {
@@ -1053,7 +1000,6 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     if (!h_actions32 || !io->actions32) return fail(MSW_ERR_NULL, "msw_step_host needs h_actions32 and io->actions32 staging");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)n, HW = (size_t)p.HW;
-    const int mode = host_mode();
 
     struct Copy { void *dst; const void *src; size_t bytes; };
     Copy copies[8] = {};
@@ -1070,12 +1016,7 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
 #define MSW_HOST_SCALAR(field, dev, type, bytes)                                                           \
     if (h && h->field) {                                                                                   \
         if (!(dev)) return fail(MSW_ERR_NULL, "host output " #field " requested without device staging"); \
-        if (mode & 2) {                                                                                    \
-            void *m = nullptr;                                                                             \
-            if ((rc = mapped_ptr(&m, h->field, "host output " #field " is not mapped pinned memory"))) return rc; \
-            dev = static_cast<type *>(m);                                                                  \
-        } else                                                                                             \
-            d2h(h->field, dev, bytes);                                                                     \
+        d2h(h->field, dev, bytes);                                                                         \
     }
     if (h && h->obs) {
         if (!p.obs) return fail(MSW_ERR_NULL, "host output obs requested without device staging");
@@ -1093,13 +1034,9 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     MSW_HOST_SCALAR(revealed_count, p.rcount, int32_t, N * 4)
 #undef MSW_HOST_SCALAR
 
-    if (mode & 1) {
-        void *m = nullptr;
-        if ((rc = mapped_ptr(&m, h_actions32, "h_actions32 is not mapped pinned memory"))) return rc;
-        p.a32 = static_cast<const int32_t *>(m);
-    } else {
-        MSW_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(io->actions32), h_actions32, N * 4, cudaMemcpyHostToDevice, s));
-    }
+    // (Letting the kernel read the actions from / write the scalars to mapped pinned memory was measured and lost:
+    // 196 / 213 / 276 us per step against 155 us with two DMAs, profiles/r01e_e2e_transfer_plans.txt -- removed.)
+    MSW_CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t *>(io->actions32), h_actions32, N * 4, cudaMemcpyHostToDevice, s));
     if ((rc = launch_env<MODE_STEP>(p, s))) return rc;
     for (int i = 0; i < nc; ++i)
         MSW_CUDA_TRY(cudaMemcpyAsync(copies[i].dst, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToHost, s));

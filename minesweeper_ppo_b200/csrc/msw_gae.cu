@@ -308,23 +308,23 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
     if (T < 0 || N < 0) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: T=%lld N=%lld", (long long)T, (long long)N);
     if (T == 0 || N == 0) return MSW_OK;
     // 32 columns per CTA (one full 128-byte line per row).  16 columns -- twice the CTAs, so every SM
-    // has work at N = 8,192 -- was measured slower (18.4 vs 14.3 us, half-line requests); it stays
-    // selectable through MSW_GAE_COLS=16 for experiments.
-    static const int forced = [] {
-        const char *e = getenv("MSW_GAE_COLS");
-        return e ? atoi(e) : 0;
-    }();
-    const int cols = forced == 16 ? 16 : 32;
+    // has work at N = 8,192 -- was measured slower (18.4 vs 14.3 us, half-line requests) and removed.
+    const int cols = 32;
     const long long blocks = (N + cols - 1) / cols;
     if (blocks > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gae: N too large");
-    // TMA path: the tensor maps need 16-byte aligned bases and row pitches (N bytes for dones).
-    // MSW_GAE_TMA=0 forces the plain-load kernel (measurements, and the path for ragged N).
+    // TMA kernel where the tensor maps can be built (16-byte aligned bases and row pitches: N % 16 == 0, N bytes
+    // for dones); the plain-load kernel serves ragged N.  One kernel per shape class, no run-time switch
+    // (-DMSW_DEV_KNOBS: MSW_GAE_TMA=0 forces the plain kernel for tools/ measurements).
+#ifdef MSW_DEV_KNOBS
     static const bool tma_on = [] {
         const char *e = getenv("MSW_GAE_TMA");
         return !(e && e[0] == '0');
     }();
+#else
+    constexpr bool tma_on = true;
+#endif
     const uintptr_t bases = (uintptr_t)rewards | (uintptr_t)values | (uintptr_t)dones | (uintptr_t)advantages | (uintptr_t)returns;
-    if (tma_on && forced == 0 && N % 16 == 0 && (bases & 15u) == 0 && T <= 0x7fffffffLL && encode_tiled_fn()) {
+    if (tma_on && N % 16 == 0 && (bases & 15u) == 0 && T <= 0x7fffffffLL && encode_tiled_fn()) {
         CUtensorMap mr, mv, md, ma, mt;
         if (!make_map(&mr, rewards, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
             !make_map(&mv, values, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
@@ -332,12 +332,7 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
             !make_map(&ma, advantages, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
             !make_map(&mt, returns, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N))
             return fail(MSW_ERR_ARG, "msw_gae: cuTensorMapEncodeTiled failed (T=%lld N=%lld)", (long long)T, (long long)N);
-        static thread_local bool configured = false;
-        if (!configured) {
-            MSW_CUDA_TRY(cudaFuncSetAttribute(gae_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(TmaGaeSmem)));
-            configured = true;
-        }
+        MSW_SET_MAX_SMEM(gae_tma_kernel, sizeof(TmaGaeSmem));
         gae_tma_kernel<<<(unsigned)blocks, TG_THREADS, sizeof(TmaGaeSmem), (cudaStream_t)stream>>>(
             mr, mv, md, ma, mt, last_values, T, N, gamma_f32, gamma_lam_f32, (int)last_values_prescaled);
         MSW_CUDA_TRY(cudaGetLastError());
@@ -347,8 +342,7 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
     gae_kernel<C><<<(unsigned)blocks, GAE_THREADS, 0, (cudaStream_t)stream>>>(                  \
         rewards, values, dones, last_values, advantages, returns, T, N, gamma_f32, gamma_lam_f32, \
         (int)last_values_prescaled)
-    if (cols == 16) MSW_GAE_LAUNCH(16);
-    else            MSW_GAE_LAUNCH(32);
+    MSW_GAE_LAUNCH(32);
 #undef MSW_GAE_LAUNCH
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;

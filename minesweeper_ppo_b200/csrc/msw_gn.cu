@@ -523,11 +523,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     if (pool32 && (size_t)(256 / (C / 8)) * C * sizeof(float) > tile_bytes) tile_bytes = (size_t)(256 / (C / 8)) * C * sizeof(float);
     const size_t smem = tile_bytes + (2 * (size_t)G + 3 * 256) * sizeof(float);
     if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act: sample of %zu bytes does not fit shared memory", smem);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(gn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
+    if (smem > 48 * 1024) MSW_SET_MAX_SMEM(gn_act_kernel, 200 * 1024);
     GnParams p;
     p.x = (const __half *)x16; p.cbias = conv_bias; p.res = res32; p.gamma = gamma; p.beta = beta;
     p.y16 = (__half *)y16; p.y32 = y32;
@@ -540,12 +536,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.epoch = epoch;
     p.pool = pool32;
     p.tile_bytes = (unsigned)tile_bytes;
-    // MSW_GN_BULK=0 selects the per-thread cp.async / STG path (measurements: profiles/r01g_gn_bulk.txt)
-    static const int bulk = [] {
-        const char *e = getenv("MSW_GN_BULK");
-        return e ? atoi(e) : 1;
-    }();
-    p.bulk = bulk;
+    p.bulk = 1;      // one cp.async.bulk per sample (the per-thread cp.async / STG path measured 6 % slower: profiles/r01g_gn_bulk.txt)
     if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))
         return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;
@@ -578,11 +569,7 @@ extern "C" int msw_gn_act_bwd(const void *x16, const float *conv_bias, const flo
     p.scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     const size_t smem = (size_t)HW * C * 2 + (2 * (size_t)G + 256 + 3 * (size_t)p.PPB * C) * sizeof(float);
     if (smem > 200 * 1024) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act_bwd: sample of %zu bytes does not fit shared memory", smem);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(gn_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
+    if (smem > 48 * 1024) MSW_SET_MAX_SMEM(gn_act_bwd_kernel, 200 * 1024);
     if (n > 0x7fffffffLL) return fail(MSW_ERR_BAD_SHAPE, "msw_gn_act_bwd: n too large");
     gn_act_bwd_kernel<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(p);
     MSW_CUDA_TRY(cudaGetLastError());

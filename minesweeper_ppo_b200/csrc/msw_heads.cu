@@ -161,14 +161,8 @@ static int launch_heads(const void *a16, const void *w1, const void *b1, const v
                         void *out_policy, void *out_mine, int64_t R, cudaStream_t stream)
 {
     const size_t smem = sizeof(HeadsSmem<C>);
-    static thread_local bool configured = false;
-    if (!configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(heads_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int dev = 0, sms = 0;
-    MSW_CUDA_TRY(cudaGetDevice(&dev));
-    MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MSW_SET_MAX_SMEM(heads_kernel<C>, smem);
+    const int sms = sm_count();
     const long long tiles = (R + HEADS_ROWS - 1) / HEADS_ROWS;
     const long long resident = (C <= 96 ? 2LL : 1LL) * sms;             // persistent grid, one wave
     const long long grid = tiles < resident ? tiles : resident;
@@ -196,20 +190,10 @@ extern "C" int msw_cell_heads(const void *a16, const void *w1, const void *b1, c
         return fail(MSW_ERR_ALIGN, "msw_cell_heads: a16 and w1 must be 16-byte aligned");
     if (rows == 0) return MSW_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    // MSW_HEADS=mma selects the mma.sync kernel of this file also where the tcgen05 kernel applies
-    static const bool want_tc = [] {
-        const char *e = getenv("MSW_HEADS");
-        return !(e && e[0] == 'm');
-    }();
-    if (want_tc) {
-        const int rc = heads_tc_launch(C, a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
-        if (rc >= 0) return rc;
-    }
-    switch (C) {
-    case 32: return launch_heads<32>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
-    case 64: return launch_heads<64>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
-    case 96: return launch_heads<96>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
-    case 128: return launch_heads<128>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
-    default: return fail(MSW_ERR_BAD_SHAPE, "msw_cell_heads: C=%d (supported: 32, 64, 96, 128)", C);
-    }
+    // one kernel per width: tcgen05 (msw_heads_tc.cu) for C = 64 / 96 / 128, whose N = 2C fills an MMA tile;
+    // the mma.sync kernel of this file only for C = 32
+    if (C == 32) return launch_heads<32>(a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
+    const int rc = heads_tc_launch(C, a16, w1, b1, w2, b2, out_policy, out_mine, rows, s);
+    if (rc >= 0) return rc;
+    return fail(MSW_ERR_BAD_SHAPE, "msw_cell_heads: C=%d (supported: 32, 64, 96, 128)", C);
 }

@@ -245,14 +245,8 @@ static int launch_heads_tc(const void *a16, const void *w1, const void *b1, cons
     CUtensorMap ma, mw;
     if (!tc_make_map(&ma, a16, R, C, TC_ROWS) || !tc_make_map(&mw, w1, Cfg::N, C, Cfg::N))
         return fail(MSW_ERR_ARG, "msw_cell_heads: cuTensorMapEncodeTiled failed (rows=%lld C=%d)", (long long)R, C);
-    static thread_local bool configured = false;
-    if (!configured) {
-        MSW_CUDA_TRY(cudaFuncSetAttribute(heads_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::BYTES));
-        configured = true;
-    }
-    int dev = 0, sms = 0;
-    MSW_CUDA_TRY(cudaGetDevice(&dev));
-    MSW_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MSW_SET_MAX_SMEM(heads_tc_kernel<C>, Cfg::BYTES);
+    const int sms = sm_count();
     const long long tiles = (R + TC_ROWS - 1) / TC_ROWS;
     const long long grid = tiles < sms ? tiles : sms;                   // persistent, one CTA (all 512 TMEM columns) per SM
     heads_tc_kernel<C><<<(unsigned)grid, TC_THREADS, Cfg::BYTES, stream>>>(

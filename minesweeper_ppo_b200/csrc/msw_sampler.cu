@@ -68,7 +68,7 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
 #pragma unroll
     for (int j = 0; j < MAXC; ++j) {
         if (j < chunk) {
-            const float e = (lo + j < A) ? __expf(v[j] - mx) : 0.0f;
+            const float e = (lo + j < A) ? expf(v[j] - mx) : 0.0f;
             v[j] = e;
             s += e;
         }
@@ -113,7 +113,7 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
     if (lane == 0) {
         // log_prob = logit - max - log(sum exp(logit - max))  (Categorical normalisation)
         const float x = mrow[action] ? to_f32<T>(lrow[action]) : neg_inf;
-        la = (x - mx) - __logf(total);
+        la = (x - mx) - logf(total);
         if (a64) a64[row] = action;
         if (a32) a32[row] = action;
         if (logp) logp[row] = la;

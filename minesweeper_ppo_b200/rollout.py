@@ -91,7 +91,15 @@ class RolloutCollector:
         self.use_graph = bool(graph)
         self._graph = None
         self._graph_aux = None
+        self._graph_key_captured = None
         self._epoch = torch.zeros(1, dtype=torch.int32, device=dev) if self.use_graph else None
+
+    def _graph_key(self, model: nn.Module, autocast: bool):
+        """Everything the captured graph bakes in besides the tensors it reads: the module object, train / eval
+        mode, every Dropout2d probability, whether aux maps are produced, the autocast flag and the env's shape.
+        A change re-captures (weights are NOT part of the key: the graph refreshes them in place every replay)."""
+        drops = tuple(float(mod.p) for mod in model.modules() if isinstance(mod, (nn.Dropout, nn.Dropout2d)))
+        return (id(model), bool(model.training), drops, self.aux_maps, bool(autocast), self.vec.num_envs, self.steps)
 
     @staticmethod
     def can_graph(model: nn.Module) -> bool:
@@ -104,7 +112,8 @@ class RolloutCollector:
             return self._collect(model, autocast)
         if not (self.fused and autocast and FusedRolloutForward.supports(model)):
             raise ValueError("graph=True needs the fused forward (CNNResidualPolicy, fused=True, CUDA autocast)")
-        if self._graph is None or self._fused_fwd.model is not model:
+        key = self._graph_key(model, autocast)
+        if self._graph is None or self._graph_key_captured != key:
             side = torch.cuda.Stream(device=self.vec.device)
             side.wait_stream(torch.cuda.current_stream(self.vec.device))
             with torch.cuda.stream(side):                       # warm-up outside capture (cuDNN plans, lazy inits)
@@ -115,7 +124,7 @@ class RolloutCollector:
             with torch.cuda.graph(g):
                 self._epoch.add_(1)
                 _, aux = self._collect(model, autocast)
-            self._graph, self._graph_aux = g, aux
+            self._graph, self._graph_aux, self._graph_key_captured = g, aux, key
         self._graph.replay()
         self.buffer._t = self.steps
         return self.buffer, dict(self._graph_aux)

@@ -145,19 +145,61 @@ class FlatGradAllReduce:
     reference, so AdamW skips them) are packed into one flat bucket (~3.8 MB for the medium
     model), summed over ranks, averaged and unpacked."""
 
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, time_it: bool = False):
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.numel = sum(p.numel() for p in self.params)
+        # The bucket layout is FIXED at the first sync (the parameters that have a gradient then); every later
+        # step packs exactly that set, a rank whose minibatch produced no gradient for one of them (e.g. the
+        # mine head when no label cell is valid) contributes zeros, and a parameter that turns up with a
+        # gradient outside the set is an error -- so all ranks always reduce buffers of the same size.
+        self._active = None
+        self._flat = None
+        self.time_it = bool(time_it)
+        self._events = []          # (start, end) CUDA events around each all-reduce when time_it
 
     def sync(self) -> None:
         if self.world <= 1:
             return
-        gs = [p.grad for p in self.params if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in gs])
+        if self._active is None:
+            self._active = [p for p in self.params if p.grad is not None]
+            sizes = torch.tensor([len(self._active), sum(p.numel() for p in self._active)], dtype=torch.int64,
+                                 device=self._active[0].device)
+            lo, hi = sizes.clone(), sizes.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("FlatGradAllReduce: ranks disagree on which parameters have gradients "
+                                   f"(min {lo.tolist()}, max {hi.tolist()})")
+            self._flat = torch.empty(int(sizes[1]), dtype=self._active[0].grad.dtype, device=sizes.device)
+            self._ids = {id(p) for p in self._active}
+        for p in self.params:
+            if p.grad is not None and id(p) not in self._ids:
+                raise RuntimeError("FlatGradAllReduce: a parameter outside the bucket fixed at the first step has a gradient")
+        flat, off = self._flat, 0
+        for p in self._active:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        if self.time_it:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if self.time_it:
+            e1.record()
+            self._events.append((e0, e1))
         flat.div_(self.world)
+        gs = [p.grad for p in self._active]
         torch._foreach_copy_(gs, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in gs]), gs)])
+
+    def allreduce_ms(self, skip: int = 0):
+        """Mean / max device time of one all-reduce (after `skip` warm-up calls); needs time_it=True."""
+        ev = self._events[skip:]
+        if not ev:
+            return None
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return {"mean_ms": sum(ms) / len(ms), "max_ms": max(ms), "calls": len(ms)}
 
 
 def ppo_update(model, optimizer, batch, cfg: PPOConfig, scaler=None, grads: Optional[FlatGradAllReduce] = None,
@@ -184,13 +226,14 @@ def ppo_update(model, optimizer, batch, cfg: PPOConfig, scaler=None, grads: Opti
 
 
 def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], steps: Optional[int], seed: int = 0,
-          log: Callable[[str], None] = print, fused_train: bool = True) -> Dict[str, float]:
+          log: Callable[[str], None] = print, fused_train: bool = True, time_allreduce: bool = False) -> Dict[str, float]:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1 and not dist.is_initialized():
+    own_group = world > 1 and not dist.is_initialized()
+    if own_group:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     cfg, env_d, model_d, extras = load_config(config)
@@ -214,7 +257,7 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
                      max_grad_norm=cfg.max_grad_norm, beta_l2=float((extras.get("training") or {}).get("beta_l2", 0.0)))
     need_aux = pcfg.aux_mine_weight > 0 or pcfg.aux_mine_calib_weight > 0
     collector = RolloutCollector(vec, T, aux_maps=need_aux, sample_seed=seed, graph=RolloutCollector.can_graph(model))
-    grads = FlatGradAllReduce(model)
+    grads = FlatGradAllReduce(model, time_it=time_allreduce)
     mb = (n_local * T) // cfg.mini_batches
     opt_step = [0]
     train_fwd = None
@@ -269,7 +312,10 @@ def train(config: Optional[str], updates: int, envs_per_gpu: Optional[int], step
         "training_forward": ("fused GroupNorm fwd+bwd (msw_gn_act / msw_gn_act_bwd), trunk conv fwd + dgrad on tcgen05 (msw_conv3x3)"
                              if train_fwd else "eager module"),
     }
-    if world > 1:
+    if time_allreduce and world > 1:
+        torch.cuda.synchronize()
+        result["grad_allreduce"] = grads.allreduce_ms(skip=cfg.ppo_epochs * cfg.mini_batches * timed_from)
+    if own_group:
         dist.destroy_process_group()
     return result if rank == 0 else {}
 
