@@ -128,6 +128,6 @@ def test_unmodified_evaluate_vec_on_cuda_env():
     pol = P.scripted_policy(16, 16).cuda()
     want2, got2 = _run_eval_both(pol, 96, 32, 1)
     _metrics_equal(want2, got2)
-    assert want2["avg_steps"] > 5.0
+    assert want2["avg_steps"] > 3.0
     print("C1 (random-init medium policy):", got)
     print("C1 (scripted policy):", got2)
