@@ -232,8 +232,9 @@ int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *m
  * norm; statistics and arithmetic in fp32; y16 (fp16 NHWC, the next conv's
  * input) and/or y32 (fp32 NHWC, the residual stream) are written.  Needs
  * C % 8 == 0 and (C/G) % 8 == 0; drop_p > 0 applies a Dropout2d channel mask
- * keyed by (seed, call_id [+ *epoch in the high word], sample, channel) and is
- * only allowed without res32.  pool32 (nullable, fp32 [n][C]) receives the
+ * keyed by (seed, call_id [+ *epoch in the high word], sample_id_base + sample,
+ * channel) -- the GLOBAL sample index, so masks do not depend on how envs are
+ * sharded over GPUs -- and is only allowed without res32.  pool32 (nullable, fp32 [n][C]) receives the
  * mean over HW of the fp32 output -- the AdaptiveAvgPool2d(1) that opens the
  * value head (cnn_residual.py:65) -- so the last block need not write y32. */
 int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
@@ -241,7 +242,7 @@ int msw_gn_act(const void *x16, const float *conv_bias, const float *res32,
                void *y16, float *y32, int64_t n, int32_t HW, int32_t C, int32_t G,
                float eps, int32_t relu, float drop_p, uint64_t seed, uint64_t call_id,
                const uint32_t *epoch, float *save_mean, float *save_rstd,
-               uint8_t *save_mask, float *pool32, void *stream);
+               uint8_t *save_mask, float *pool32, int64_t sample_id_base, void *stream);
 
 /* Input of the stem convolution: fp32 NCHW observation planes obs [n][Cin][HW] (Cin <= 16; the env's 10
  * planes) -> fp16 NHWC out16 [n][HW][16] with the missing channels zero, i.e. the autocast cast of
@@ -277,9 +278,9 @@ int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int
  * (Round 1: correct but slower than the two calls it replaces -- see DESIGN.md 4.5c; the rollout forward
  * uses it only with MSW_CONV_GN=1.) */
 int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
-                   const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
-                   int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed,
-                   uint64_t call_id, const uint32_t *epoch, void *stream);
+                   const float *gamma, const float *beta, void *y16, float *y32, float *pool4, int64_t n,
+                   int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p,
+                   uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, void *stream);
 
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and
@@ -298,20 +299,40 @@ int msw_gn_act_bwd(const void *x16, const float *conv_bias, const float *gamma,
 
 /* Host-buffer form of msw_step for callers that keep the reference's NumPy
  * calling convention (VecMinesweeper.step(actions: np.ndarray), env.py:479):
- * `h_actions32` and every non-NULL h_* output are pinned host buffers; `io`
- * holds the device staging buffers (same meaning as msw_step; io->actions32
- * is the device staging buffer for the actions).  Copies actions in, runs the
- * step, copies the requested outputs back and synchronises `stream`. */
+ * `h_actions32` and the non-NULL per-env scalar outputs are pinned host
+ * buffers; `io` holds the device staging buffers (same meaning as msw_step;
+ * io->actions32 is the device staging buffer for the actions; io->enc may be
+ * all NULL).  Copies actions in, runs the step, copies the requested scalars
+ * back and synchronises `stream`.
+ *
+ * obs / mask (the arrays VecMinesweeper.step returns, env.py:507-510: fp32
+ * [n][10][H][W] and bool [n][HW]) are ORDINARY host memory and are not copied
+ * over PCIe: the packed post-step state they are a pure function of (mines,
+ * revealed, meta: 2*wpb + 4 words per env, 80 B instead of 10.5 KB at 16x16)
+ * is copied into `stage` (pinned, n*(2*wpb + 4) int32) and expanded on
+ * `threads` host threads (0 = every CPU the process may run on) after the
+ * sync.  That is a format conversion of the GPU's result; no game logic runs
+ * on the host. */
 typedef struct msw_host_out {
-    float   *obs;                  /* nullable */
-    uint8_t *mask;                 /* nullable */
+    float   *obs;                  /* nullable; ordinary host memory */
+    uint8_t *mask;                 /* nullable; ordinary host memory */
     float   *reward;               /* nullable */
     uint8_t *done;                 /* nullable */
     int8_t  *outcome;              /* nullable */
     int32_t *new_reveals;          /* nullable */
     int32_t *step;                 /* nullable */
     int32_t *revealed_count;       /* nullable */
+    int32_t *stage;                /* pinned, required when obs or mask is set */
+    int32_t  threads;
+    int32_t  reserved;
 } msw_host_out;
+
+/* The host-side expansion on its own: packed state arrays IN HOST MEMORY (h_mines / h_revealed int32 [n][wpb],
+ * h_meta int32 [n][4], layouts of msw_state) -> _build_obs (env.py:172-192) / _compute_action_mask
+ * (env.py:194-196) arrays in host memory.  Pure host function (no CUDA call), used by msw_step_host and by
+ * VecMinesweeper.reset() in the NumPy convention. */
+int msw_expand_obs_host(const msw_env_desc *desc, const int32_t *h_mines, const int32_t *h_revealed,
+                        const int32_t *h_meta, int64_t n, float *h_obs, uint8_t *h_mask, int32_t threads);
 
 int msw_step_host(const msw_env_desc *desc, const msw_state *st,
                   const msw_step_io *io, const int32_t *h_actions32,

@@ -1,7 +1,7 @@
 // msw_conv_tc.cu -- 3x3 "same" convolution of the policy trunk (96 -> 96 channels on 16x16 boards, and the stem's
 // 16 -> 96; fp16 NHWC in, fp32 accumulate, fp16 NHWC out) on the 5th-generation tensor cores, plain
 // (conv3x3_tc_kernel<false>: no bias, it is folded into msw_gn_act) or with GroupNorm / ReLU / Dropout2d /
-// residual add fused into the epilogue (conv3x3_tc_kernel<true>).
+// residual add (and the value head's average pool) fused into the epilogue (conv3x3_tc_kernel<true>).
 //
 // out[y][x][co] = sum_{dy,dx,ci} in[y+dy][x+dx][ci] * w[co][ci][dy][dx] is computed as nine shifted GEMMs
 // per 128-pixel tile (8 image rows of one board) that all accumulate into ONE TMEM accumulator.  The tile's
@@ -61,14 +61,29 @@ struct Cfg {
 }  // namespace cv
 
 // What the fused GroupNorm epilogue needs (conv3x3_tc_kernel<true>); same meaning as msw_gn_act's arguments.
+//
+// The fp32 residual stream (res32 in, y32 out) is private to this kernel family, so it lives in HBM in the order
+// the epilogue touches it -- "P8": [board][tile 2][channel third 3][8-channel chunk 4][pixel 128][8 floats].  A
+// thread (= pixel) owns one 32-byte chunk per (third, chunk); the 32 lanes of a warp are 32 consecutive pixels,
+// so every 256-bit load / store instruction of a warp covers 1 KB of consecutive addresses (8 full lines)
+// instead of one line per lane as the pixel-major NHWC order would (32 lines per instruction: the epilogue was
+// LSU-bound at 690 us per layer with it, against 240 us of MMAs).
 struct ConvGnParams {
     const float *cbias, *gamma, *beta;   // [96]
-    const float *res32;                  // nullable [n][256][96]
-    float *y32;                          // nullable [n][256][96]
+    const float *res32;                  // nullable, P8 order
+    float *y32;                          // nullable, P8 order
+    float *pool4;                        // nullable [n][4][96]: per row-quarter sums of the fp32 output (value head's avg pool)
     float eps, drop_p, drop_scale;
     uint32_t k0, k1, call_lo, call_hi;
     const uint32_t *epoch;               // nullable
+    long long sample_base;               // global index of board 0 (Dropout2d stream is keyed by the global board)
 };
+
+// float offset of (board, tile, third, chunk, pixel-in-tile) in the P8 order
+__device__ __forceinline__ long long cv_p8(long long board, int half, int third, int c4, int pp)
+{
+    return ((((board * 2 + half) * 3 + third) * 4 + c4) * 128 + pp) * 8;
+}
 
 __device__ __forceinline__ unsigned cv_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cv_bar_init(unsigned bar, unsigned count)
@@ -148,7 +163,9 @@ __device__ __forceinline__ float cv_warp_sum(float v)          // fixed shuffle 
 // GN = false: out = conv(x) (fp16).  GN = true: out = relu(GroupNorm(conv(x) + bias) [+ res]) [* Dropout2d], the
 // whole inter-convolution step of msw_gn_act fused into the epilogue (6 groups of 16 channels; statistics over
 // the board = the CTA's two consecutive tiles, whose fp16-rounded conv outputs wait in registers).
-template <bool GN, int CIN>
+// EPI (GN only): 0 = no residual (Dropout2d allowed, y32 optional), 1 = residual in, y32 out, 2 = residual in, pooled
+// sums out (the last block: nothing reads its residual stream but the value head's average pool).
+template <bool GN, int CIN, int EPI>
 __global__ void __launch_bounds__(cv::THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
@@ -299,9 +316,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // Dropout2d scale of channel `te` for this board (msw_gn_act's stream: Philox keyed by board and 8-channel
             // chunk).  It does not depend on the data, so it is drawn here, off the path between the two barriers.
             float sc = gp.drop_scale;
-            if (te < C && gp.drop_p > 0.0f) {
+            if (EPI == 0 && te < C && gp.drop_p > 0.0f) {
                 uint32_t w[4];
-                philox4x32_10(gp.k0, gp.k1 ^ 0x44524f50u, (uint32_t)board, (uint32_t)(board >> 32) ^ (uint32_t)(te >> 3), gp.call_lo,
+                const long long gb = gp.sample_base + board;
+                philox4x32_10(gp.k0, gp.k1 ^ 0x44524f50u, (uint32_t)gb, (uint32_t)(gb >> 32) ^ (uint32_t)(te >> 3), gp.call_lo,
                               gp.call_hi + (gp.epoch ? *gp.epoch : 0u), w);
                 const int k = te & 7;
                 const uint32_t u16 = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
@@ -314,8 +332,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const unsigned it = 2u * bi + half, acc = it % ACC, aph = (it / ACC) & 1u;
-                if (gp.res32)     // this pixel's 128-byte line of the residual stream: on its way to L2 while the tile is drained
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(gp.res32 + (board * 256 + half * 128 + q * 32 + lane) * (long long)C + cbase));
+                if (EPI != 0)     // the 16 KB of residual stream this warpgroup will read for this tile: one line per thread on its way to L2
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(gp.res32 + cv_p8(board, half, third, 0, 0) + (q * 32 + lane) * 32));
                 cv_bar_wait(tfull(acc), aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t lo[16], hi[16];
@@ -374,42 +392,69 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 s_ab[(par * 2 + 1) * C + c] = fmaf(s_cb[c] - mg, a, gp.beta[c]) * sc;
             }
             asm volatile("bar.sync 1, 384;" ::: "memory");
-            // ---- normalise, (+ residual), ReLU, store: both tiles
+            // ---- normalise, (+ residual), ReLU, store: chunk by chunk (8 channels), both tiles per chunk
             const float4 *a4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 0) * C + cbase);
             const float4 *b4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 1) * C + cbase);
-            uint32_t rnext[8];                       // residual values of the next 8-channel chunk: loaded one chunk ahead
-            if (gp.res32) cv_ld256(gp.res32 + (board * 256 + q * 32 + lane) * (long long)C + cbase, rnext);
+            const int pp = q * 32 + lane;
+            uint32_t rnext[8];                       // residual values of the next (chunk, tile): loaded one step ahead
+            if (EPI != 0) cv_ld256(gp.res32 + cv_p8(board, 0, third, 0, pp), rnext);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const long long px = board * 256 + half * 128 + q * 32 + lane;
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                const float4 aa0 = a4[c0 >> 2], aa1 = a4[(c0 >> 2) + 1], bb0 = b4[c0 >> 2], bb1 = b4[(c0 >> 2) + 1];
+                const float av[8] = {aa0.x, aa0.y, aa0.z, aa0.w, aa1.x, aa1.y, aa1.z, aa1.w};
+                const float bv[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+                float ps[8];                         // EPI 2: this thread's two pixels summed, per channel
 #pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    const float4 aa0 = a4[c0 >> 2], aa1 = a4[(c0 >> 2) + 1], bb0 = b4[c0 >> 2], bb1 = b4[(c0 >> 2) + 1];
-                    const float av[8] = {aa0.x, aa0.y, aa0.z, aa0.w, aa1.x, aa1.y, aa1.z, aa1.w};
-                    const float bv[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+                for (int half = 0; half < 2; ++half) {
                     uint32_t rr[8];
-                    if (gp.res32) {
+                    if (EPI != 0) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) rr[k] = rnext[k];
-                        if (c0 < 24) cv_ld256(gp.res32 + px * C + cbase + c0 + 8, rnext);
-                        else if (half == 0) cv_ld256(gp.res32 + (px + 128) * C + cbase, rnext);
+                        if (half == 0) cv_ld256(gp.res32 + cv_p8(board, 1, third, c0 >> 3, pp), rnext);
+                        else if (c0 < 24) cv_ld256(gp.res32 + cv_p8(board, 0, third, (c0 >> 3) + 1, pp), rnext);
                     }
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
                         const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h[half][(c0 + j) >> 1]));
                         float v0 = fmaf(f.x, av[j], bv[j]), v1 = fmaf(f.y, av[j + 1], bv[j + 1]);
-                        if (gp.res32) { v0 += __uint_as_float(rr[j]); v1 += __uint_as_float(rr[j + 1]); }
-                        o[j] = __float_as_uint(fmaxf(v0, 0.0f));
-                        o[j + 1] = __float_as_uint(fmaxf(v1, 0.0f));
+                        if (EPI != 0) { v0 += __uint_as_float(rr[j]); v1 += __uint_as_float(rr[j + 1]); }
+                        v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f);
+                        o[j] = __float_as_uint(v0);
+                        o[j + 1] = __float_as_uint(v1);
+                        if (EPI == 2) {
+                            ps[j] = half == 0 ? v0 : ps[j] + v0;
+                            ps[j + 1] = half == 0 ? v1 : ps[j + 1] + v1;
+                        }
                     }
-                    if (gp.y32) cv_st256(gp.y32 + px * C + cbase + c0, o);
+                    if (EPI != 2 && gp.y32) cv_st256(gp.y32 + cv_p8(board, half, third, c0 >> 3, pp), o);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1]));
                         h[half][(c0 >> 1) + k] = *reinterpret_cast<const uint32_t *>(&hh);     // reuse the slot for the output
                     }
                 }
+                if (EPI == 2) {
+                    // warp sum of 8 channels over the 32 lanes in 9 shuffles (fixed butterfly: deterministic): each
+                    // step halves the number of channels a lane carries; lane L ends with channel bit4*4 + bit3*2 + bit2
+                    const bool b4s = lane & 16, b3s = lane & 8, b2s = lane & 4;
+                    float a1[4], a2[2], a3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        a1[i] = (b4s ? ps[4 + i] : ps[i]) + __shfl_xor_sync(0xffffffffu, b4s ? ps[i] : ps[4 + i], 16);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        a2[i] = (b3s ? a1[2 + i] : a1[i]) + __shfl_xor_sync(0xffffffffu, b3s ? a1[i] : a1[2 + i], 8);
+                    a3 = (b2s ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2s ? a2[0] : a2[1], 4);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, 2);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, 1);
+                    if ((lane & 3) == 0)
+                        gp.pool4[(board * 4 + q) * C + cbase + c0 + (b4s ? 4 : 0) + (b3s ? 2 : 0) + (b2s ? 1 : 0)] = a3;
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const long long px = board * 256 + half * 128 + pp;
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
                     uint32_t packed[8];
@@ -449,16 +494,16 @@ static CvEncodeFn cv_encode_fn()
 
 }  // namespace msw
 
-template <bool GN, int CIN>
+template <bool GN, int CIN, int EPI>
 static int conv_launch_t(const CUtensorMap &ma0, const CUtensorMap &ma1, const CUtensorMap &mw0, const CUtensorMap &mw1, void *y16,
                          int64_t n, int dbg, const msw::ConvGnParams &gp, cudaStream_t stream)
 {
     using namespace msw;
     using K = cv::Cfg<CIN>;
-    MSW_SET_MAX_SMEM((conv3x3_tc_kernel<GN, CIN>), K::SMEM_BYTES);
+    MSW_SET_MAX_SMEM((conv3x3_tc_kernel<GN, CIN, EPI>), K::SMEM_BYTES);
     const int sms = sm_count();
     const long long grid = n < sms ? n : sms;                       // persistent: whole boards per CTA
-    conv3x3_tc_kernel<GN, CIN><<<(unsigned)grid, cv::THREADS, K::SMEM_BYTES, stream>>>(ma0, ma1, mw0, mw1, (__half *)y16,
+    conv3x3_tc_kernel<GN, CIN, EPI><<<(unsigned)grid, cv::THREADS, K::SMEM_BYTES, stream>>>(ma0, ma1, mw0, mw1, (__half *)y16,
                                                                                        (long long)n, dbg, gp);
     MSW_CUDA_TRY(cudaGetLastError());
     return MSW_OK;
@@ -513,14 +558,16 @@ static int conv_launch(const char *who, const void *x16, const void *w_taps16, v
         if (r0 != CUDA_SUCCESS || (Cin == 96 && r1 != CUDA_SUCCESS))
             return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
     }
-    const int dbg = 0;
+    const int dbg = 0;      // (bit 0 skips the plain epilogue's stores: used once to time the MMA + TMA part alone)
     const ConvGnParams none = {};
     const ConvGnParams &gp = gn ? *gn : none;
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin == 96) return gn ? conv_launch_t<true, 96>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
-                             : conv_launch_t<false, 96>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
-    return gn ? conv_launch_t<true, 16>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
-              : conv_launch_t<false, 16>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+    if (!gn) return Cin == 96 ? conv_launch_t<false, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
+                              : conv_launch_t<false, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+    if (Cin == 16) return conv_launch_t<true, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);          // the stem has no residual
+    if (!gp.res32) return conv_launch_t<true, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+    return gp.pool4 ? conv_launch_t<true, 96, 2>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
+                    : conv_launch_t<true, 96, 1>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
 }
 
 extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
@@ -530,22 +577,26 @@ extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int
 }
 
 extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
-                              const float *gamma, const float *beta, void *y16, float *y32, int64_t n, int32_t H,
-                              int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p, uint64_t seed,
-                              uint64_t call_id, const uint32_t *epoch, void *stream)
+                              const float *gamma, const float *beta, void *y16, float *y32, float *pool4, int64_t n,
+                              int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p,
+                              uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, void *stream)
 {
     using namespace msw;
     if (!conv_bias || !gamma || !beta) return fail(MSW_ERR_NULL, "msw_conv3x3_gn: NULL pointer");
     if (G != 6) return fail(MSW_ERR_BAD_SHAPE, "msw_conv3x3_gn: needs 6 groups of 16 channels (G=%d)", G);
     if (drop_p < 0.0f || drop_p >= 1.0f) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: drop_p=%f", drop_p);
     if (drop_p > 0.0f && res32) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: dropout is only defined on the no-residual path");
+    if (Cin != 96 && res32) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: the residual path needs Cin = 96");
+    if (pool4 && (!res32 || y32)) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: pool4 replaces y32 on the residual path");
+    if (res32 && !pool4 && !y32) return fail(MSW_ERR_ARG, "msw_conv3x3_gn: the residual path writes y32 or pool4");
     if ((((uintptr_t)res32 | (uintptr_t)y32) & 31u) != 0)
         return fail(MSW_ERR_ALIGN, "msw_conv3x3_gn: res32 / y32 must be 32-byte aligned");
     ConvGnParams g;
-    g.cbias = conv_bias; g.gamma = gamma; g.beta = beta; g.res32 = res32; g.y32 = y32;
+    g.cbias = conv_bias; g.gamma = gamma; g.beta = beta; g.res32 = res32; g.y32 = y32; g.pool4 = pool4;
     g.eps = eps; g.drop_p = drop_p; g.drop_scale = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
     g.call_lo = (uint32_t)call_id; g.call_hi = (uint32_t)(call_id >> 32);
     g.epoch = epoch;
+    g.sample_base = (long long)sample_id_base;
     return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, Cin, C, &g, stream);
 }

@@ -22,6 +22,10 @@
 
 namespace msw {
 
+// msw_host_expand.cu: packed state -> the reference's fp32 observation planes / bool mask, on host threads
+void expand_obs_host(int H, int W, const uint32_t *mines, const uint32_t *revealed, const int32_t *meta, long long n,
+                     float *obs, uint8_t *mask, int threads);
+
 struct EnvParams {
     int H, W, HW, wpb;
     int mine_count, safe;
@@ -1018,13 +1022,16 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
         if (!(dev)) return fail(MSW_ERR_NULL, "host output " #field " requested without device staging"); \
         d2h(h->field, dev, bytes);                                                                         \
     }
-    if (h && h->obs) {
-        if (!p.obs) return fail(MSW_ERR_NULL, "host output obs requested without device staging");
-        d2h(h->obs, p.obs, N * MSW_OBS_CHANNELS * HW * 4);
-    }
-    if (h && h->mask) {
-        if (!p.mask) return fail(MSW_ERR_NULL, "host output mask requested without device staging");
-        d2h(h->mask, p.mask, N * HW);
+    // Reference-shaped observation / mask on the host: NOT copied (41*HW bytes per env would make the call
+    // PCIe-bound); the packed post-step state they are a pure function of (2*wpb + 4 words per env) is copied
+    // into the caller's pinned staging area and expanded on the host after the sync (msw_host_expand.cu).
+    const bool expand = h && (h->obs || h->mask);
+    const size_t wpb = (size_t)p.wpb;
+    if (expand) {
+        if (!h->stage) return fail(MSW_ERR_NULL, "msw_step_host: host obs/mask requested without the pinned state staging area");
+        d2h(h->stage, st->mines, N * wpb * 4);
+        d2h(h->stage + N * wpb, st->revealed, N * wpb * 4);
+        d2h(h->stage + 2 * N * wpb, st->meta, N * 16);
     }
     MSW_HOST_SCALAR(reward, p.reward, float, N * 4)
     MSW_HOST_SCALAR(done, p.done, uint8_t, N)
@@ -1041,6 +1048,9 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     for (int i = 0; i < nc; ++i)
         MSW_CUDA_TRY(cudaMemcpyAsync(copies[i].dst, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToHost, s));
     MSW_CUDA_TRY(cudaStreamSynchronize(s));
+    if (expand)
+        expand_obs_host(p.H, p.W, reinterpret_cast<const uint32_t *>(h->stage), reinterpret_cast<const uint32_t *>(h->stage + N * wpb),
+                        h->stage + 2 * N * wpb, (long long)n, h->obs, h->mask, h->threads);
     return MSW_OK;
 }
 

@@ -70,6 +70,7 @@ struct GnParams {
     float *save_mean, *save_rstd;   // [n][G] statistics of (x + conv_bias)
     uint8_t *save_mask;             // [n][HW][C/8]: bit k of a byte = output channel 8j+k is "on" (ReLU active, not dropped)
     float *pool;                    // nullable [n][C]: mean over HW of the fp32 output (AdaptiveAvgPool2d(1) of the value head)
+    long long sample_base;          // global index of sample 0: the Dropout2d stream is keyed by the GLOBAL sample (shard-invariant)
 };
 
 __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long long n_samples)
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(256, 4) gn_act_kernel(const GnParams p, long l
             uint32_t kept = 0xFFu;                                    // channels that survive Dropout2d
             uint32_t w[4] = {0u, 0u, 0u, 0u};
             if (p.drop_p > 0.0f)
-                philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)n, (uint32_t)(n >> 32) ^ (uint32_t)j, p.call_lo,
-                              p.call_hi + (p.epoch ? *p.epoch : 0u), w);
+                philox4x32_10(p.k0, p.k1 ^ 0x44524f50u, (uint32_t)(n + p.sample_base),
+                              (uint32_t)((n + p.sample_base) >> 32) ^ (uint32_t)j, p.call_lo, p.call_hi + (p.epoch ? *p.epoch : 0u), w);
             const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -508,7 +509,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
                           const float *beta, void *y16,
                           float *y32, int64_t n, int32_t HW, int32_t C, int32_t G, float eps, int32_t relu,
                           float drop_p, uint64_t seed, uint64_t call_id, const uint32_t *epoch, float *save_mean,
-                          float *save_rstd, uint8_t *save_mask, float *pool32, void *stream)
+                          float *save_rstd, uint8_t *save_mask, float *pool32, int64_t sample_id_base, void *stream)
 {
     using namespace msw;
     if (!x16 || !gamma || !beta || (!y16 && !y32 && !pool32)) return fail(MSW_ERR_NULL, "msw_gn_act: NULL pointer");
@@ -535,6 +536,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.call_lo = (uint32_t)call_id; p.call_hi = (uint32_t)(call_id >> 32);
     p.epoch = epoch;
     p.pool = pool32;
+    p.sample_base = (long long)sample_id_base;
     p.tile_bytes = (unsigned)tile_bytes;
     p.bulk = 1;      // one cp.async.bulk per sample (the per-thread cp.async / STG path measured 6 % slower: profiles/r01g_gn_bulk.txt)
     if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))

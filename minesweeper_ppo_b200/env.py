@@ -194,6 +194,7 @@ class VecMinesweeper:
         self._pinned: Dict[str, torch.Tensor] = {}
         self._host_calls: Dict[Any, Any] = {}
         self._pinned_ok: set = set()
+        self._result_pool: list = []
         self._staging: Dict[str, torch.Tensor] = {}
         # late-start curriculum (env.py:397-403, 416-466): parameters normalised as the reference does
         self._late = None
@@ -464,13 +465,12 @@ class VecMinesweeper:
         self.mine_labels, self.mine_valid = o.mine_labels, o.mine_valid
         return {"obs": o.obs, "action_mask": o.action_mask}, rewards, dones, infos
 
-    # reference calling convention: NumPy in / NumPy out through pinned host buffers
+    # reference calling convention: NumPy in / NumPy out (msw_step_host)
     def _host_buffers(self) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor]]:
         if not self._pinned:
-            n, H, W, HW, dev = self.num_envs, self.H, self.W, self.HW, self.device
+            n, dev = self.num_envs, self.device
             spec = {
-                "actions": ((n,), torch.int32), "obs": ((n, OBS_CHANNELS, H, W), torch.float32),
-                "mask": ((n, HW), torch.bool), "reward": ((n,), torch.float32), "done": ((n,), torch.bool),
+                "actions": ((n,), torch.int32), "reward": ((n,), torch.float32), "done": ((n,), torch.bool),
                 "outcome": ((n,), torch.int8), "new_reveals": ((n,), torch.int32), "step": ((n,), torch.int32),
                 "revealed_count": ((n,), torch.int32),
             }
@@ -494,15 +494,38 @@ class VecMinesweeper:
                 else:
                     self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
                     self._staging["h_" + k] = torch.empty(shape, dtype=dt, device=dev)
-            if self.aux_maps:
-                self._staging["h_labels"] = torch.empty((n, H, W), dtype=torch.float32, device=dev)
-                self._staging["h_valid"] = torch.empty((n, H, W), dtype=torch.bool, device=dev)
+            # packed post-step state (mines | revealed | meta): what obs / mask are expanded from on the host
+            self._pinned["stage"] = torch.empty((n * (2 * self.wpb + 4),), dtype=torch.int32).pin_memory()
         return self._pinned, self._staging
 
-    def step_host(self, actions_pinned: torch.Tensor, *, copy_obs: bool = True, copy_infos: bool = True
-                  ) -> Dict[str, torch.Tensor]:
-        """msw_step_host: pinned int32 actions in; pinned outputs back (obs/mask optional);
-        synchronises the current stream.  Returns the pinned tensors (valid until the next call)."""
+    @staticmethod
+    def host_obs_d2h_bytes(H: int, W: int, n: int) -> int:
+        """Device->host bytes per step of the reference calling convention: packed state + reward + done
+        (the fp32 planes are expanded on the host, they do not cross PCIe)."""
+        wpb = (H * W + 31) // 32
+        return n * ((2 * wpb + 4) * 4 + 5)
+
+    def _result_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(obs f32 [n,10,H,W], mask bool [n,HW]) for the next result.  The reference returns fresh arrays every
+        call (np.stack, env.py:507-510); fresh 688 MB allocations would cost more in page faults than the whole
+        step, so arrays are recycled from a small pool -- but ONLY when nobody else references them any more
+        (any view / torch.from_numpy alias keeps a reference to its base array), otherwise a new one is made."""
+        import sys
+        for k, (o, m) in enumerate(self._result_pool):
+            if sys.getrefcount(o) <= 3 and sys.getrefcount(m) <= 3:      # pool tuple + loop variable + getrefcount argument
+                return o, m
+        o = np.empty((self.num_envs, OBS_CHANNELS, self.H, self.W), np.float32)
+        m = np.empty((self.num_envs, self.HW), bool)
+        if len(self._result_pool) < 4:
+            self._result_pool.append((o, m))
+        return o, m
+
+    def step_host(self, actions_pinned: torch.Tensor, *, copy_obs: bool = True, copy_infos: bool = True,
+                  out: Optional[Tuple[np.ndarray, np.ndarray]] = None, threads: int = 0) -> Dict[str, Any]:
+        """msw_step_host: pinned int32 actions in; per-env scalars back in pinned buffers; with copy_obs the
+        reference-shaped obs / mask NumPy arrays ("obs", "mask" of the result: `out` if given, else recycled
+        arrays) are filled by the host-side expansion of the packed state.  Synchronises the current stream.
+        The returned pinned tensors are valid until the next call."""
         n = self.num_envs
         pin, st = self._host_buffers()
         ap = actions_pinned.data_ptr()
@@ -521,19 +544,34 @@ class VecMinesweeper:
             io.reward, io.done = st["h_reward"].data_ptr(), st["h_done"].data_ptr()
             io.outcome, io.new_reveals = st["h_outcome"].data_ptr(), st["h_new_reveals"].data_ptr()
             io.step, io.revealed_count = st["h_step"].data_ptr(), st["h_revealed_count"].data_ptr()
-            io.enc.obs, io.enc.mask = st["h_obs"].data_ptr(), st["h_mask"].data_ptr()
-            io.enc.mine_labels = st["h_labels"].data_ptr() if self.aux_maps else None
-            io.enc.mine_valid = st["h_valid"].data_ptr() if self.aux_maps else None
+            io.enc.obs = io.enc.mask = None                    # no device-side encode: the planes are made on the host
+            if self.aux_maps:                                  # device-resident aux maps for a device consumer
+                if "h_labels" not in st:
+                    st["h_labels"] = torch.empty((n, self.H, self.W), dtype=torch.float32, device=self.device)
+                    st["h_valid"] = torch.empty((n, self.H, self.W), dtype=torch.bool, device=self.device)
+                io.enc.mine_labels, io.enc.mine_valid = st["h_labels"].data_ptr(), st["h_valid"].data_ptr()
+            else:
+                io.enc.mine_labels = io.enc.mine_valid = None
             h = _lib.HostOut()
             h.reward, h.done = pin["reward"].data_ptr(), pin["done"].data_ptr()
-            if copy_obs:
-                h.obs, h.mask = pin["obs"].data_ptr(), pin["mask"].data_ptr()
             if copy_infos:
                 h.outcome, h.new_reveals = pin["outcome"].data_ptr(), pin["new_reveals"].data_ptr()
                 h.step, h.revealed_count = pin["step"].data_ptr(), pin["revealed_count"].data_ptr()
+            h.stage = pin["stage"].data_ptr()
             prepared = self._host_calls[key] = (io, h, C.byref(self._desc), C.byref(self._state), C.byref(io),
                                                 C.byref(h))
         io, h, r_desc, r_state, r_io, r_h = prepared
+        res: Dict[str, Any] = dict(pin)
+        if copy_obs:
+            obs, mask = out if out is not None else self._result_arrays()
+            if (obs.dtype != np.float32 or obs.shape != (n, OBS_CHANNELS, self.H, self.W) or not obs.flags.c_contiguous
+                    or mask.dtype != np.bool_ or mask.shape != (n, self.HW) or not mask.flags.c_contiguous):
+                raise ValueError("step_host: out must be (float32 [n,10,H,W], bool [n,HW]) C-contiguous arrays")
+            h.obs, h.mask = obs.ctypes.data, mask.ctypes.data
+            res["obs"], res["mask"] = obs, mask
+        else:
+            h.obs = h.mask = None
+        h.threads = int(threads)
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
         if torch.cuda.current_device() == self.device.index:
@@ -547,7 +585,7 @@ class VecMinesweeper:
         self._cache = None
         if self.aux_maps:
             self.mine_labels, self.mine_valid = st["h_labels"], st["h_valid"]
-        return pin
+        return res
 
     def _step_numpy(self, actions) -> Tuple[Dict[str, np.ndarray], np.ndarray, np.ndarray, Dict[str, Any]]:
         n = self.num_envs
@@ -563,32 +601,29 @@ class VecMinesweeper:
             dones = d.cpu().numpy()
             outcome, newr = info["outcome_code"].cpu().numpy(), info["last_new_reveals"].cpu().numpy()
             step, rc = info["step"].cpu().numpy(), info["revealed_count"].cpu().numpy()
-            infos = {
-                "aux": [{"step": int(step[i]), "last_new_reveals": int(newr[i]),
-                         "revealed_frac": float(int(rc[i]) / max(1, self.HW))} for i in range(n)],
-                "outcome": [_OUTCOME_NAMES[int(outcome[i])] for i in range(n)],
-                "done": [bool(dones[i]) for i in range(n)],
-            }
-            return ({"obs": b["obs"].cpu().numpy(), "action_mask": b["action_mask"].cpu().numpy()},
-                    r.cpu().numpy(), dones, infos)
-        pin, _ = self._host_buffers()
-        a = actions.astype(np.int64, copy=False)
-        # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32
-        if a.size and (a.max() > 2**31 - 1 or a.min() < -2**31):
-            a = np.mod(a, self.HW)
-        pin["actions"].numpy()[:] = a
-        self.step_host(pin["actions"])
-        rewards = pin["reward"].numpy().copy()
-        dones = pin["done"].numpy().copy()
-        outcome, newr = pin["outcome"].numpy(), pin["new_reveals"].numpy()
-        step, rc = pin["step"].numpy(), pin["revealed_count"].numpy()
+            batch = {"obs": b["obs"].cpu().numpy(), "action_mask": b["action_mask"].cpu().numpy()}
+            rewards = r.cpu().numpy()
+        else:
+            pin, _ = self._host_buffers()
+            a = actions.astype(np.int64, copy=False)
+            # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32
+            if a.size and (a.max() > 2**31 - 1 or a.min() < -2**31):
+                a = np.mod(a, self.HW)
+            pin["actions"].numpy()[:] = a
+            res = self.step_host(pin["actions"])
+            rewards = pin["reward"].numpy().copy()
+            dones = pin["done"].numpy().copy()
+            outcome, newr = pin["outcome"].numpy(), pin["new_reveals"].numpy()
+            step, rc = pin["step"].numpy(), pin["revealed_count"].numpy()
+            batch = {"obs": res["obs"], "action_mask": res["mask"]}
+            del res
+        hw = max(1, self.HW)
         infos = {                                                     # env.py:485-505
-            "aux": [{"step": int(step[i]), "last_new_reveals": int(newr[i]),
-                     "revealed_frac": float(int(rc[i]) / max(1, self.HW))} for i in range(n)],
-            "outcome": [_OUTCOME_NAMES[int(outcome[i])] for i in range(n)],
-            "done": [bool(dones[i]) for i in range(n)],
+            "aux": [{"step": s_, "last_new_reveals": r_, "revealed_frac": c_ / hw}
+                    for s_, r_, c_ in zip(step.tolist(), newr.tolist(), rc.tolist())],
+            "outcome": [_OUTCOME_NAMES[o] for o in outcome.tolist()],
+            "done": dones.tolist(),
         }
-        batch = {"obs": pin["obs"].numpy().copy(), "action_mask": pin["mask"].numpy().copy()}
         return batch, rewards, dones, infos
 
     # ------------------------------------------------------------------ raw state (native API)

@@ -10,8 +10,6 @@ fp32 tensors (the fp16 casts are part of the graph), so AdamW / GradScaler / cli
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn.functional as F
 
@@ -44,7 +42,7 @@ class GnAct(torch.autograd.Function):
                               gamma.data_ptr(), beta.data_ptr(), y16.data_ptr(), None if y32 is None else y32.data_ptr(),
                               N, H * W, C, groups, float(eps), int(relu), float(drop_p), int(seed) & (2**64 - 1),
                               int(call_id) & (2**64 - 1), None, mean.data_ptr(), rstd.data_ptr(), mask.data_ptr(),
-                              None, torch.cuda.current_stream(dev).cuda_stream)
+                              None, 0, torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "msw_gn_act")
         ctx.save_for_backward(x16, cb, gamma, mean, rstd, mask)
         ctx.meta = (groups, float(drop_p), res32 is not None)
@@ -114,8 +112,7 @@ class Conv3x3Tc(torch.autograd.Function):
 
 
 def _conv3(x16: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
-    if (conv.in_channels == 96 and conv.out_channels == 96 and tuple(x16.shape[2:]) == (16, 16)
-            and os.environ.get("MSW_CONV", "tc") != "cudnn"):
+    if conv.in_channels == 96 and conv.out_channels == 96 and tuple(x16.shape[2:]) == (16, 16):
         return Conv3x3Tc.apply(x16, conv.weight)
     w16 = conv.weight.to(torch.float16).contiguous(memory_format=_CL)      # differentiable cast
     return F.conv2d(x16, w16, None, padding=1)

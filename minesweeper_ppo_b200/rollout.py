@@ -144,7 +144,7 @@ class RolloutCollector:
         fwd = model
         if self.fused and autocast and FusedRolloutForward.supports(model):
             if self._fused_fwd is None or self._fused_fwd.model is not model:
-                self._fused_fwd = FusedRolloutForward(model, seed=self.sample_seed)
+                self._fused_fwd = FusedRolloutForward(model, seed=self.sample_seed, sample_id_base=vec._desc.env_id_base)
                 self._fused_fwd.epoch = self._epoch
             self._fused_fwd.refresh()                         # weights may have been updated since
             fwd, ctx = self._fused_fwd, nullcontext

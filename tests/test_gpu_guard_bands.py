@@ -90,7 +90,7 @@ def test_sampler_and_gn_outputs_stay_inside_their_windows(A, n):
     rpl, pool, npl = _window(torch, (n, C), torch.float32)
     gn = torch.nn.GroupNorm(G, C).cuda()
     rc = L.msw_gn_act(x.data_ptr(), None, None, gn.weight.data_ptr(), gn.bias.data_ptr(), y16.data_ptr(), y32.data_ptr(),
-                      n, H * W, C, G, 1e-5, 1, 0.0, 0, 0, None, None, None, None, pool.data_ptr(),
+                      n, H * W, C, G, 1e-5, 1, 0.0, 0, 0, None, None, None, None, pool.data_ptr(), 0,
                       torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()

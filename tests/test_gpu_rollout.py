@@ -205,13 +205,21 @@ def test_conv3x3_matches_cudnn(n, cin):
             assert torch.equal(one, ref), (ky, kx)
 
 
-@pytest.mark.parametrize("n,res,drop", [(3, False, 0.0), (149, True, 0.0), (300, False, 0.25), (7, True, 0.0)])
-def test_conv3x3_gn_matches_unfused(n, res, drop):
-    """msw_conv3x3_gn vs msw_conv3x3 followed by msw_gn_act on the same operands: same fp16 rounding point of
-    the conv output, same Dropout2d stream; the group statistics are reduced in a different order, so the fp32
-    output agrees to a few ulp and the fp16 one to one fp16 ulp."""
+@pytest.mark.parametrize("n,res,drop,pool", [(3, False, 0.0, False), (149, True, 0.0, False), (300, False, 0.25, False),
+                                             (7, True, 0.0, False), (5, True, 0.0, True), (301, True, 0.0, True)])
+def test_conv3x3_gn_matches_torch_fp32(n, res, drop, pool):
+    """msw_conv3x3_gn (conv + GroupNorm [+ fp32 residual] + ReLU [+ Dropout2d] [+ average pool] in one tcgen05
+    launch, cnn_residual.py:17-27) against the same expression in plain torch fp32:
+        relu(group_norm(fp16(conv_fp32(x16, w16)) + bias) [+ res])
+    -- the conv result rounded to fp16 where autocast rounds it, everything after it in fp32.  The only freedom
+    is the summation order of the fp32 accumulator (a conv output may land on the other side of an fp16 rounding
+    boundary: 1 fp16 ulp of a unit-scale value, scaled by gamma * rstd <= ~2).  The residual stream and the fp32
+    output use the kernels' private P8 order (fused_forward.to_p8 / from_p8).  The unfused pair
+    msw_conv3x3 -> msw_gn_act is kept as a second, tighter reference (identical fp16 conv rounding)."""
     import torch
-    from minesweeper_ppo_b200.fused_forward import conv3x3, conv3x3_gn, conv3x3_taps, gn_act
+    import torch.nn.functional as F
+    from minesweeper_ppo_b200.fused_forward import conv3x3, conv3x3_gn, conv3x3_taps, from_p8, gn_act, to_p8
+    torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device="cuda").manual_seed(n)
     C = 96
     x = torch.randn((n, C, 16, 16), device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
@@ -220,20 +228,74 @@ def test_conv3x3_gn_matches_unfused(n, res, drop):
     norm = torch.nn.GroupNorm(6, C).cuda()
     with torch.no_grad():
         norm.weight.uniform_(0.5, 1.5); norm.bias.uniform_(-0.3, 0.3)
-    r = (torch.randn((n, C, 16, 16), device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
-         if res else None)
+    r = torch.randn((n, C, 16, 16), device="cuda", generator=g) if res else None
+    r_p8 = to_p8(r) if res else None
+    assert not res or torch.equal(from_p8(r_p8), r)                      # the layout helpers are inverses
     taps = conv3x3_taps(w)
-    want16, want32 = gn_act(conv3x3(x, taps), norm, conv_bias=bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
-    got16, got32 = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
-    again16, again32 = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=True, seed=5, call_id=77)
-    assert torch.equal(got16, again16) and torch.equal(got32, again32)
+    kw = dict(res32=r_p8, drop_p=drop, seed=5, call_id=77, sample_id_base=1000)
+    got16, got2 = conv3x3_gn(x, taps, norm, bias, want32=not pool, want_pool=pool, **kw)
+    again16, again2 = conv3x3_gn(x, taps, norm, bias, want32=not pool, want_pool=pool, **kw)
+    assert torch.equal(got16, again16) and torch.equal(got2, again2), "bitwise reproducible"
+    # ---- torch fp32 reference
+    with torch.no_grad():
+        conv16 = F.conv2d(x.float(), w.float(), None, padding=1).half()
+        z = F.group_norm(conv16.float() + bias.view(1, C, 1, 1), 6, norm.weight, norm.bias, norm.eps)
+        want32 = torch.relu(z + r if res else z)
     scale = float(want32.abs().max()) + 1.0
-    assert float((got32 - want32).abs().max()) <= 2e-5 * scale
-    assert float((got16.float() - want16.float()).abs().max()) <= 2e-3 * scale
-    if drop > 0:                                             # the same channels are dropped
-        assert torch.equal(got32.abs().sum(dim=(2, 3)) == 0, want32.abs().sum(dim=(2, 3)) == 0)
-    only16, none = conv3x3_gn(x, taps, norm, bias, res32=r, drop_p=drop, want32=False, seed=5, call_id=77)
+    if drop > 0:      # Dropout2d: whole channels of a board zeroed, survivors scaled by 1/(1-p); mask = the kernel's stream
+        got32 = from_p8(got2)
+        dropped = got32.abs().sum(dim=(2, 3)) == 0
+        frac = float((dropped & (want32.abs().sum(dim=(2, 3)) > 0)).float().mean())
+        assert 0.18 < frac < 0.32, frac
+        want32 = torch.where(dropped[:, :, None, None], torch.zeros_like(want32), want32 / (1.0 - drop))
+        scale = float(want32.abs().max()) + 1.0
+    if pool:
+        assert got2.shape == (n, C)
+        assert float((got2 - want32.mean(dim=(2, 3))).abs().max()) <= 1e-3 * scale
+    else:
+        got32 = from_p8(got2)
+        assert float((got32 - want32).abs().max()) <= 4e-3 * scale
+        assert float((got32 - want32).abs().mean()) <= 2e-5 * scale          # boundary flips are rare
+        assert torch.equal(got16, got32.half().contiguous(memory_format=torch.channels_last))
+    assert float((got16.float() - want32).abs().max()) <= 5e-3 * scale
+    # ---- the unfused pair: same fp16 conv output bit for bit, so only the statistics' reduction order differs
+    u16, u32 = gn_act(conv3x3(x, taps), norm, conv_bias=bias, res32=(r.contiguous(memory_format=torch.channels_last) if res else None),
+                      drop_p=drop, want32=True, seed=5, call_id=77, sample_id_base=1000)
+    uscale = float(u32.abs().max()) + 1.0
+    if pool:
+        assert float((got2 - u32.mean(dim=(2, 3))).abs().max()) <= 2e-5 * uscale
+    else:
+        assert float((from_p8(got2) - u32).abs().max()) <= 2e-5 * uscale
+        if drop > 0:                                             # the same channels are dropped by both kernels
+            assert torch.equal(from_p8(got2).abs().sum(dim=(2, 3)) == 0, u32.abs().sum(dim=(2, 3)) == 0)
+    assert float((got16.float() - u16.float()).abs().max()) <= 2e-3 * uscale
+    only16, none = conv3x3_gn(x, taps, norm, bias, want32=False, **kw) if not res else (got16, None)
     assert none is None and torch.equal(only16, got16)
+
+
+def test_dropout_stream_is_keyed_by_global_sample():
+    """Dropout2d masks depend on sample_id_base + local index (the global env id), not on the local index:
+    a shard starting at 40 draws what rows 40.. of an unsharded call draw (shard invariance of the rollout)."""
+    import torch
+    from minesweeper_ppo_b200.fused_forward import conv3x3_gn, conv3x3_taps, gn_act
+    g = torch.Generator(device="cuda").manual_seed(0)
+    C, n = 96, 64
+    x = torch.randn((n, C, 16, 16), device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((C, C, 3, 3), device="cuda", generator=g) / (9 * C) ** 0.5).half()
+    bias = torch.zeros((C,), device="cuda")
+    norm = torch.nn.GroupNorm(6, C).cuda()
+    taps = conv3x3_taps(w)
+    full, _ = conv3x3_gn(x, taps, norm, bias, drop_p=0.3, seed=1, call_id=2, sample_id_base=0)
+    part, _ = conv3x3_gn(x[40:].contiguous(memory_format=torch.channels_last), taps, norm, bias, drop_p=0.3, seed=1, call_id=2,
+                         sample_id_base=40)
+    assert torch.equal(full[40:], part)
+    other, _ = conv3x3_gn(x[40:].contiguous(memory_format=torch.channels_last), taps, norm, bias, drop_p=0.3, seed=1, call_id=2,
+                          sample_id_base=0)
+    assert not torch.equal(full[40:], other)
+    z = x
+    f2, _ = gn_act(z, norm, drop_p=0.3, seed=1, call_id=2, sample_id_base=0)
+    p2, _ = gn_act(z[40:].contiguous(memory_format=torch.channels_last), norm, drop_p=0.3, seed=1, call_id=2, sample_id_base=40)
+    assert torch.equal(f2[40:], p2)
 
 
 def test_gn_act_pooled_output():
