@@ -390,8 +390,12 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         "e2e_host_obs": {
             "value": total_envs * Kh / e2e_full_max, "unit": UNIT, "steps": Kh,
             "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": host_obs_d2h_bytes(m, N),
-            "call": "same call with copy_obs=True: the full reference-shaped NumPy result (obs+mask+reward+done) "
-                    "in host memory every step",
+            "call": "same call with copy_obs=True: the full reference-shaped NumPy result (obs fp32 [N,10,H,W] + mask + "
+                    "reward + done) in host memory every step.  The planes do not cross PCIe: msw_step_host copies the "
+                    "packed post-step state (85 B/env) and expands it on all host threads with non-temporal stores "
+                    "(msw_host_expand.cu); the call is bound by host memory store bandwidth "
+                    f"({(41 * H * W) * N / 1e6:.0f} MB written per step)",
+            "host_threads": host_threads(),
         },
         "gpu_launches": K,
         "gae": gae_info,

@@ -218,8 +218,10 @@ int msw_gae(const float *rewards, const float *values, const uint8_t *dones,
  * (seed, row_id_base + row, step_index), and log_prob(action) is returned.
  * `epoch` (nullable device uint32) is added to the high word of step_index when
  * the kernel runs, so a captured CUDA graph draws fresh numbers on each replay.
- * Writes whichever of actions64 / actions32 / logp is non-NULL. */
-int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *mask,
+ * Writes whichever of actions64 / actions32 / logp is non-NULL.  `mask` is in/out
+ * for one case only: a row without any legal action is made all-legal (and
+ * sampled as such), the collector's guard of train_rl.py:166-168 / 263-265. */
+int msw_masked_sample(const void *logits, int32_t logits_dtype, uint8_t *mask,
                       int64_t n, int32_t A, uint64_t seed, uint64_t step_index,
                       const uint32_t *epoch, int64_t row_id_base, int64_t *actions64,
                       int32_t *actions32, float *logp, void *stream);
@@ -271,16 +273,22 @@ int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int
                 int32_t Cin, int32_t C, void *stream);
 
 /* msw_conv3x3 with msw_gn_act fused into its epilogue: one launch for "convolution, GroupNorm, (+ fp32
- * residual), ReLU, Dropout2d" of a residual block half (cnn_residual.py:17-27).  Arguments as in the two
- * calls it replaces: y16 = fp16(relu(GN(conv(x16) + conv_bias) [+ res32]) [* Dropout2d]), y32 (nullable) the
- * same in fp32; the conv output is rounded to fp16 before the norm exactly as the unfused path (and the
- * autocast reference) does; Dropout2d draws the same stream as msw_gn_act.  16x16 boards, C = 96, G = 6.
- * (Round 1: correct but slower than the two calls it replaces -- see DESIGN.md 4.5c; the rollout forward
- * uses it only with MSW_CONV_GN=1.) */
+ * residual), ReLU, Dropout2d" of a residual block half (cnn_residual.py:17-27):
+ *   y16 = fp16(relu(GN(fp16(conv(x16)) + conv_bias) [+ res32]) [* Dropout2d]),  y32 (nullable) the same in fp32;
+ * the conv output is rounded to fp16 before the norm exactly as the autocast reference does; Dropout2d draws
+ * msw_gn_act's stream, keyed by sample_id_base + board.  16x16 boards, C = 96, G = 6, Cin = 96 or 16 (the stem).
+ * res32 (nullable; Cin = 96 only) and y32 are in the kernels' PRIVATE "P8" order -- [n][tile 2][channel third 3]
+ * [8-channel chunk 4][pixel-in-tile 128][8] floats -- in which every 256-bit access of a warp is one contiguous
+ * KB (the pixel-major NHWC order costs one line per lane); only this function reads or writes that stream.
+ * pool4 (nullable, with res32, instead of y32): fp32 [n][4][C] per-row-quarter sums of the fp32 output, whose sum
+ * over the 4 quarters / 256 is the AdaptiveAvgPool2d(1) of the value head (cnn_residual.py:65).
+ * max_ctas: 0 = one persistent CTA per SM; k > 0 caps the grid so that two launches on different streams can
+ * share the GPU (FusedRolloutForward overlaps an HBM-bound residual layer with an MMA-bound one that way). */
 int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
                    const float *gamma, const float *beta, void *y16, float *y32, float *pool4, int64_t n,
                    int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p,
-                   uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, void *stream);
+                   uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, int32_t max_ctas,
+                   void *stream);
 
 /* Backward of msw_gn_act for the training forward.  save_mean / save_rstd
  * ([n][G]) and save_mask ([n][HW][C/8], bit k = channel 8j+k passed ReLU and

@@ -496,12 +496,13 @@ static CvEncodeFn cv_encode_fn()
 
 template <bool GN, int CIN, int EPI>
 static int conv_launch_t(const CUtensorMap &ma0, const CUtensorMap &ma1, const CUtensorMap &mw0, const CUtensorMap &mw1, void *y16,
-                         int64_t n, int dbg, const msw::ConvGnParams &gp, cudaStream_t stream)
+                         int64_t n, int dbg, const msw::ConvGnParams &gp, int max_ctas, cudaStream_t stream)
 {
     using namespace msw;
     using K = cv::Cfg<CIN>;
     MSW_SET_MAX_SMEM((conv3x3_tc_kernel<GN, CIN, EPI>), K::SMEM_BYTES);
-    const int sms = sm_count();
+    int sms = sm_count();
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;             // caller shares the GPU with a concurrent launch
     const long long grid = n < sms ? n : sms;                       // persistent: whole boards per CTA
     conv3x3_tc_kernel<GN, CIN, EPI><<<(unsigned)grid, cv::THREADS, K::SMEM_BYTES, stream>>>(ma0, ma1, mw0, mw1, (__half *)y16,
                                                                                        (long long)n, dbg, gp);
@@ -511,7 +512,7 @@ static int conv_launch_t(const CUtensorMap &ma0, const CUtensorMap &ma1, const C
 
 // Shared host side of msw_conv3x3 / msw_conv3x3_gn: argument checks, the four tensor maps, the launch.
 static int conv_launch(const char *who, const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
-                       int32_t Cin, int32_t C, const msw::ConvGnParams *gn, void *stream)
+                       int32_t Cin, int32_t C, const msw::ConvGnParams *gn, int max_ctas, void *stream)
 {
     using namespace msw;
     if (!x16 || !w_taps16 || !y16) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
@@ -562,24 +563,25 @@ static int conv_launch(const char *who, const void *x16, const void *w_taps16, v
     const ConvGnParams none = {};
     const ConvGnParams &gp = gn ? *gn : none;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!gn) return Cin == 96 ? conv_launch_t<false, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
-                              : conv_launch_t<false, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
-    if (Cin == 16) return conv_launch_t<true, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);          // the stem has no residual
-    if (!gp.res32) return conv_launch_t<true, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
-    return gp.pool4 ? conv_launch_t<true, 96, 2>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st)
-                    : conv_launch_t<true, 96, 1>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, st);
+    if (!gn) return Cin == 96 ? conv_launch_t<false, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st)
+                              : conv_launch_t<false, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st);
+    if (Cin == 16) return conv_launch_t<true, 16, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st);          // the stem has no residual
+    if (!gp.res32) return conv_launch_t<true, 96, 0>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st);
+    return gp.pool4 ? conv_launch_t<true, 96, 2>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st)
+                    : conv_launch_t<true, 96, 1>(ma0, ma1, mw0, mw1, y16, n, dbg, gp, max_ctas, st);
 }
 
 extern "C" int msw_conv3x3(const void *x16, const void *w_taps16, void *y16, int64_t n, int32_t H, int32_t W,
                            int32_t Cin, int32_t C, void *stream)
 {
-    return conv_launch("msw_conv3x3", x16, w_taps16, y16, n, H, W, Cin, C, nullptr, stream);
+    return conv_launch("msw_conv3x3", x16, w_taps16, y16, n, H, W, Cin, C, nullptr, 0, stream);
 }
 
 extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float *conv_bias, const float *res32,
                               const float *gamma, const float *beta, void *y16, float *y32, float *pool4, int64_t n,
                               int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t G, float eps, float drop_p,
-                              uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, void *stream)
+                              uint64_t seed, uint64_t call_id, const uint32_t *epoch, int64_t sample_id_base, int32_t max_ctas,
+                              void *stream)
 {
     using namespace msw;
     if (!conv_bias || !gamma || !beta) return fail(MSW_ERR_NULL, "msw_conv3x3_gn: NULL pointer");
@@ -598,5 +600,5 @@ extern "C" int msw_conv3x3_gn(const void *x16, const void *w_taps16, const float
     g.call_lo = (uint32_t)call_id; g.call_hi = (uint32_t)(call_id >> 32);
     g.epoch = epoch;
     g.sample_base = (long long)sample_id_base;
-    return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, Cin, C, &g, stream);
+    return conv_launch("msw_conv3x3_gn", x16, w_taps16, y16, n, H, W, Cin, C, &g, max_ctas, stream);
 }

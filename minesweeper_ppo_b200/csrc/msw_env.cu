@@ -933,7 +933,9 @@ static int launch_env(const EnvParams &p, cudaStream_t s)
     if (p.W == 16 && p.HW == 256)
         launch_shape<MODE, 16, 256>(p, grid, block, s);       // BASELINE configs 1-3, 5
     else if (p.W == 30 && p.HW == 480)
-        launch_shape<MODE, 30, 480>(p, grid, block, s);       // BASELINE config 4 (Expert)
+        launch_shape<MODE, 30, 480>(p, grid, block, s);       // BASELINE config 4 (Expert, H=16 W=30)
+    else if (p.W == 16 && p.HW == 480)
+        launch_shape<MODE, 16, 480>(p, grid, block, s);       // Expert transposed (H=30 W=16)
     else
         launch_shape<MODE, 0, 0>(p, grid, block, s);
     MSW_CUDA_TRY(cudaGetLastError());

@@ -35,7 +35,7 @@ template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { 
 
 template <typename T, int MAXC>
 __global__ void __launch_bounds__(128)
-masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ mask, long long n, int A,
+masked_sample_kernel(const T *__restrict__ logits, uint8_t *__restrict__ mask, long long n, int A,
                      float neg_inf_in, uint32_t k0, uint32_t k1, uint32_t step_lo, uint32_t step_hi,
                      const uint32_t *__restrict__ epoch, long long row_id_base, long long *__restrict__ a64, int32_t *__restrict__ a32,
                      float *__restrict__ logp)
@@ -47,8 +47,21 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
     const float neg_inf = round_to<T>(neg_inf_in);
     const int lo = lane * chunk;
     const T *lrow = logits + row * (long long)A;
-    const uint8_t *mrow = mask + row * (long long)A;
+    uint8_t *mrow = mask + row * (long long)A;
 
+    uint32_t mb = 0u;                                       // this lane's mask bits
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j)
+        if (j < chunk && lo + j < A && mrow[lo + j]) mb |= 1u << j;
+    // A row without a single legal action becomes all-legal, in the stored mask too (the collector's guard,
+    // train_rl.py:166-168 / 263-265; unreachable through the env, which resets finished boards).
+    const bool none = __ballot_sync(FULL, mb != 0u) == 0u;
+    if (none) {
+        mb = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j)
+            if (j < chunk && lo + j < A) mrow[lo + j] = 1;
+    }
     float v[MAXC];
     float mx = -3.0e38f;
 #pragma unroll
@@ -56,7 +69,7 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
         if (j < chunk) {
             const int i = lo + j;
             float x = -3.0e38f;
-            if (i < A) x = mrow[i] ? to_f32<T>(lrow[i]) : neg_inf;     // masked_fill (train_rl.py:232)
+            if (i < A) x = (mb >> j & 1u) ? to_f32<T>(lrow[i]) : neg_inf;     // masked_fill (train_rl.py:232)
             v[j] = x;
             mx = fmaxf(mx, x);
         }
@@ -112,7 +125,7 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
     action = __shfl_sync(FULL, action, owner);
     if (lane == 0) {
         // log_prob = logit - max - log(sum exp(logit - max))  (Categorical normalisation)
-        const float x = mrow[action] ? to_f32<T>(lrow[action]) : neg_inf;
+        const float x = (none || mrow[action]) ? to_f32<T>(lrow[action]) : neg_inf;
         la = (x - mx) - logf(total);
         if (a64) a64[row] = action;
         if (a32) a32[row] = action;
@@ -122,7 +135,7 @@ masked_sample_kernel(const T *__restrict__ logits, const uint8_t *__restrict__ m
 
 }  // namespace msw
 
-extern "C" int msw_masked_sample(const void *logits, int32_t logits_dtype, const uint8_t *mask, int64_t n,
+extern "C" int msw_masked_sample(const void *logits, int32_t logits_dtype, uint8_t *mask, int64_t n,
                                  int32_t A, uint64_t seed, uint64_t step_index, const uint32_t *epoch,
                                  int64_t row_id_base,
                                  int64_t *actions64, int32_t *actions32, float *logp, void *stream)

@@ -522,10 +522,11 @@ class VecMinesweeper:
 
     def step_host(self, actions_pinned: torch.Tensor, *, copy_obs: bool = True, copy_infos: bool = True,
                   out: Optional[Tuple[np.ndarray, np.ndarray]] = None, threads: int = 0) -> Dict[str, Any]:
-        """msw_step_host: pinned int32 actions in; per-env scalars back in pinned buffers; with copy_obs the
+        """msw_step_host: pinned int32 actions in; per-env scalars back in pinned buffers.  With copy_obs the
         reference-shaped obs / mask NumPy arrays ("obs", "mask" of the result: `out` if given, else recycled
-        arrays) are filled by the host-side expansion of the packed state.  Synchronises the current stream.
-        The returned pinned tensors are valid until the next call."""
+        arrays) are filled by the host-side expansion of the packed state; without it the kernel writes obs / mask
+        into device tensors ("obs_device", "mask_device") for a device-resident consumer.  Synchronises the current
+        stream.  The returned pinned tensors are valid until the next call."""
         n = self.num_envs
         pin, st = self._host_buffers()
         ap = actions_pinned.data_ptr()
@@ -544,7 +545,13 @@ class VecMinesweeper:
             io.reward, io.done = st["h_reward"].data_ptr(), st["h_done"].data_ptr()
             io.outcome, io.new_reveals = st["h_outcome"].data_ptr(), st["h_new_reveals"].data_ptr()
             io.step, io.revealed_count = st["h_step"].data_ptr(), st["h_revealed_count"].data_ptr()
-            io.enc.obs = io.enc.mask = None                    # no device-side encode: the planes are made on the host
+            if copy_obs:                                       # the planes are made on the host: no device-side encode
+                io.enc.obs = io.enc.mask = None
+            else:                                              # device consumer (the policy): obs / mask written to HBM
+                if "h_obs" not in st:
+                    st["h_obs"] = torch.empty((n, OBS_CHANNELS, self.H, self.W), dtype=torch.float32, device=self.device)
+                    st["h_mask"] = torch.empty((n, self.HW), dtype=torch.bool, device=self.device)
+                io.enc.obs, io.enc.mask = st["h_obs"].data_ptr(), st["h_mask"].data_ptr()
             if self.aux_maps:                                  # device-resident aux maps for a device consumer
                 if "h_labels" not in st:
                     st["h_labels"] = torch.empty((n, self.H, self.W), dtype=torch.float32, device=self.device)
@@ -562,6 +569,8 @@ class VecMinesweeper:
                                                 C.byref(h))
         io, h, r_desc, r_state, r_io, r_h = prepared
         res: Dict[str, Any] = dict(pin)
+        if not copy_obs:
+            res["obs_device"], res["mask_device"] = st["h_obs"], st["h_mask"]
         if copy_obs:
             obs, mask = out if out is not None else self._result_arrays()
             if (obs.dtype != np.float32 or obs.shape != (n, OBS_CHANNELS, self.H, self.W) or not obs.flags.c_contiguous

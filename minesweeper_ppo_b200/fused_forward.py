@@ -113,8 +113,8 @@ def from_p8(t: torch.Tensor) -> torch.Tensor:
 
 def conv3x3_gn(x16: torch.Tensor, taps16: torch.Tensor, norm: torch.nn.GroupNorm, conv_bias: torch.Tensor, *,
                res32: Optional[torch.Tensor] = None, drop_p: float = 0.0, want32: bool = False, want_pool: bool = False,
-               seed: int = 0, call_id: int = 0, epoch: Optional[torch.Tensor] = None, sample_id_base: int = 0
-               ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+               seed: int = 0, call_id: int = 0, epoch: Optional[torch.Tensor] = None, sample_id_base: int = 0,
+               max_ctas: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """msw_conv3x3_gn: relu(GroupNorm(conv3x3(x16) + bias) [+ res32]) [* Dropout2d] in one launch.
     `res32` and the fp32 output are in the P8 order (`to_p8`); with `want_pool` the second result is instead
     the spatial mean of the fp32 output, fp32 [N, C] (the value head's AdaptiveAvgPool2d(1))."""
@@ -138,7 +138,7 @@ def conv3x3_gn(x16: torch.Tensor, taps16: torch.Tensor, norm: torch.nn.GroupNorm
                               None if pool4 is None else pool4.data_ptr(), N, H, W, Cin, C, norm.num_groups,
                               float(norm.eps), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
                               int(call_id) & 0xFFFFFFFFFFFFFFFF, None if epoch is None else epoch.data_ptr(),
-                              int(sample_id_base), torch.cuda.current_stream(dev).cuda_stream)
+                              int(sample_id_base), int(max_ctas), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "msw_conv3x3_gn")
     if want_pool:
         return y16, pool4.sum(dim=1) * (1.0 / (H * W))
@@ -158,7 +158,7 @@ class FusedRolloutForward:
 
     _warned = set()
 
-    def __init__(self, model: CNNResidualPolicy, seed: int = 0, sample_id_base: int = 0):
+    def __init__(self, model: CNNResidualPolicy, seed: int = 0, sample_id_base: int = 0, overlap_halves: bool = True):
         if not isinstance(model, CNNResidualPolicy):
             raise TypeError("FusedRolloutForward supports CNNResidualPolicy only")
         C = model.stem[0].out_channels
@@ -169,6 +169,11 @@ class FusedRolloutForward:
         self.sample_id_base = int(sample_id_base)     # global index of row 0 (env shard offset): keys the Dropout2d stream
         self.epoch: Optional[torch.Tensor] = None     # device uint32 counter mixed into the dropout RNG (graph replays)
         self.tc_trunk = C == 96 and G == 6 and model.stem[0].in_channels <= 16 and len(model.residual_stack) >= 1
+        # Two half-batches on two streams, the second one layer behind the first and each launch capped at half the
+        # SMs: a residual-carrying layer (HBM-bound: 2.4 GB per layer at 8,192 boards) of one half then runs beside
+        # a no-residual layer (tensor-core-bound, 0.8 GB) of the other instead of each having the GPU to itself.
+        self.overlap_halves = bool(overlap_halves)
+        self._side: Optional[torch.cuda.Stream] = None
         self._w: List = []
         self.refresh()
 
@@ -243,28 +248,71 @@ class FusedRolloutForward:
     def _drop_p(self, blk) -> float:
         return float(blk.dropout.p) if (self.model.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
 
-    def _trunk_tc(self, obs: torch.Tensor, cid: int):
-        """Medium-config shape: 11 msw_conv3x3_gn launches; returns (a16 NHWC, pooled fp32 [N, C])."""
+    def _trunk_tc(self, obs: torch.Tensor, cid: int, sample_base: Optional[int] = None, max_ctas: int = 0, after_stem=None):
+        """Medium-config shape: 11 msw_conv3x3_gn launches; returns (a16 NHWC, pooled fp32 [N, C]).
+        `after_stem` (optional callable) runs right after the stem launch (the two-stream schedule hooks in there)."""
         m = self.model
+        base = self.sample_id_base if sample_base is None else sample_base
         nb, cin, hh, ww = obs.shape
         x = torch.empty((nb, 16, hh, ww), dtype=torch.float16, device=obs.device, memory_format=torch.channels_last)
         with torch.cuda.device(obs.device):
             _lib.check(_lib.load().msw_pack_obs16(obs.data_ptr(), x.data_ptr(), nb, cin, hh * ww,
                                                   torch.cuda.current_stream(obs.device).cuda_stream), "msw_pack_obs16")
-        a16, a32 = conv3x3_gn(x, self.stem_taps, m.stem[1], self.stem[1], want32=True)     # stem conv + GroupNorm + ReLU
+        a16, a32 = conv3x3_gn(x, self.stem_taps, m.stem[1], self.stem[1], want32=True, max_ctas=max_ctas)   # stem conv + GN + ReLU
+        if after_stem is not None:
+            after_stem()
         last = len(self.blocks) - 1
         pooled = None
         for k, (blk, ((_, b1), (_, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
             # conv1 + GroupNorm + ReLU + Dropout2d
             t16, _ = conv3x3_gn(a16, self.taps[k][0], blk.norm1, b1, drop_p=self._drop_p(blk), seed=self.seed,
-                                call_id=cid + k, epoch=self.epoch, sample_id_base=self.sample_id_base)
+                                call_id=cid + k, epoch=self.epoch, sample_id_base=base, max_ctas=max_ctas)
             # conv2 + GroupNorm + fp32 residual add + ReLU; the last block emits the value head's average pool
             # instead of a residual stream nobody reads
             if k == last:
-                a16, pooled = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want_pool=True)
+                a16, pooled = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want_pool=True, max_ctas=max_ctas)
             else:
-                a16, a32 = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want32=True)
+                a16, a32 = conv3x3_gn(t16, self.taps[k][1], blk.norm2, b2, res32=a32, want32=True, max_ctas=max_ctas)
         return a16, pooled
+
+    def _heads(self, a16: torch.Tensor, pooled: torch.Tensor, return_mine: bool):
+        n, c, h, w = a16.shape
+        rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
+        if c in (32, 64, 96, 128):
+            pol, mine = cell_heads(rows, self.head1[0], self.head1[1], self.head2[0], self.head2[1])
+        else:                                                        # other widths: the same math as library GEMMs
+            hid = F.relu_(F.linear(rows, *self.head1))               # [n*h*w, 2C]
+            pol = F.linear(hid[:, :c], self.head2[0][None, :c], self.head2[1][0:1]).squeeze(-1)
+            mine = F.linear(hid[:, c:], self.head2[0][None, c:], self.head2[1][1:2]).squeeze(-1)
+        logits = pol.reshape(n, h * w)
+        v = F.relu_(F.linear(pooled.to(torch.float16), *self.value[0]))
+        v = F.relu_(F.linear(v, *self.value[1]))
+        value = F.linear(v, *self.value[2]).squeeze(-1)
+        if not return_mine:
+            return logits, value
+        return logits, value, mine.reshape(n, 1, h, w)
+
+    def _call_two_streams(self, obs: torch.Tensor, return_mine: bool, cid: int):
+        dev = obs.device
+        cur = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        n = obs.shape[0]
+        h = n // 2
+        half = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // 2)
+        stem_done = torch.cuda.Event()
+        side.wait_stream(cur)                                        # fork: obs is ready on the current stream
+        a16, pooled = self._trunk_tc(obs[:h], cid, self.sample_id_base, half, after_stem=lambda: stem_done.record(cur))
+        out0 = self._heads(a16, pooled, return_mine)
+        with torch.cuda.stream(side):
+            side.wait_event(stem_done)                               # second half runs one layer behind the first
+            b16, bpool = self._trunk_tc(obs[h:], cid, self.sample_id_base + h, half)
+            out1 = self._heads(b16, bpool, return_mine)
+        cur.wait_stream(side)                                        # join
+        for t in out1:
+            t.record_stream(cur)
+        return tuple(torch.cat((u, v), dim=0) for u, v in zip(out0, out1))
 
     def _trunk_library(self, obs: torch.Tensor, cid: int):
         """Any other shape: cuDNN fp16 NHWC convolutions with msw_gn_act between them."""
@@ -305,21 +353,10 @@ class FusedRolloutForward:
         self.calls += 1
         cid = self.calls << 8
         if (self.tc_trunk and tuple(obs.shape[2:]) == (16, 16) and obs.dtype == torch.float32 and obs.is_contiguous()):
+            n = obs.shape[0]
+            if self.overlap_halves and n % 2 == 0 and n >= 1024:
+                return self._call_two_streams(obs, return_mine, cid)
             a16, pooled = self._trunk_tc(obs, cid)
         else:
             a16, pooled = self._trunk_library(obs, cid)
-        n, c, h, w = a16.shape
-        rows = a16.permute(0, 2, 3, 1).reshape(n * h * w, c)         # NHWC storage: a view, no copy
-        if c in (32, 64, 96, 128):
-            pol, mine = cell_heads(rows, self.head1[0], self.head1[1], self.head2[0], self.head2[1])
-        else:                                                        # other widths: the same math as library GEMMs
-            hid = F.relu_(F.linear(rows, *self.head1))               # [n*h*w, 2C]
-            pol = F.linear(hid[:, :c], self.head2[0][None, :c], self.head2[1][0:1]).squeeze(-1)
-            mine = F.linear(hid[:, c:], self.head2[0][None, c:], self.head2[1][1:2]).squeeze(-1)
-        logits = pol.reshape(n, h * w)
-        v = F.relu_(F.linear(pooled.to(torch.float16), *self.value[0]))
-        v = F.relu_(F.linear(v, *self.value[1]))
-        value = F.linear(v, *self.value[2]).squeeze(-1)
-        if not return_mine:
-            return logits, value
-        return logits, value, mine.reshape(n, 1, h, w)
+        return self._heads(a16, pooled, return_mine)

@@ -543,3 +543,32 @@ def test_fused_train_forward_gradients_match_autocast_module():
         cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
         rel = float((g - r).norm() / (r.norm() + 1e-30))
         assert cos > 0.995 and rel < 0.1, (k, cos, rel)      # both paths carry fp16 rounding noise
+
+
+def test_all_masked_row_guard():
+    """train_rl.py:166-168 / 263-265: a row whose mask has no legal action becomes all-legal before sampling
+    (and that is the mask the buffer stores).  msw_masked_sample applies the same guard in the launch: the
+    row's mask bytes are set, the action is drawn from the raw logits, logp is the unmasked log-softmax."""
+    import torch
+    from minesweeper_ppo_b200.rollout import masked_sample
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, A = 64, 256
+    logits = torch.randn((n, A), device="cuda", generator=g)
+    mask = torch.rand((n, A), device="cuda", generator=g) < 0.5
+    dead = [3, 17, 63]
+    mask[dead] = False
+    before = mask.clone()
+    a64, a32, logp = masked_sample(logits, mask, seed=1, step_index=2)
+    assert bool(mask[dead].all()), "guarded rows must come back all-legal"
+    keep = [i for i in range(n) if i not in dead]
+    assert torch.equal(mask[keep], before[keep]), "other rows untouched"
+    want = torch.log_softmax(logits[dead], dim=-1).gather(1, a64[dead].unsqueeze(1)).squeeze(1)
+    assert float((logp[dead] - want).abs().max()) < 2e-5
+    assert bool(before[keep].gather(1, a64[keep].unsqueeze(1)).all()), "live rows sample legal actions only"
+    # the guarded rows sample from ALL cells: over many draws both halves of the row are hit
+    hits = torch.zeros(A, device="cuda")
+    for s in range(200):
+        m2 = torch.zeros((1, A), dtype=torch.bool, device="cuda")
+        a, _, _ = masked_sample(torch.zeros((1, A), device="cuda"), m2, seed=s, step_index=0)
+        hits[a[0]] += 1
+    assert int((hits > 0).sum()) > 100
