@@ -158,7 +158,7 @@ class FusedRolloutForward:
 
     _warned = set()
 
-    def __init__(self, model: CNNResidualPolicy, seed: int = 0, sample_id_base: int = 0, overlap_halves: bool = True):
+    def __init__(self, model: CNNResidualPolicy, seed: int = 0, sample_id_base: int = 0, max_ctas: int = 0):
         if not isinstance(model, CNNResidualPolicy):
             raise TypeError("FusedRolloutForward supports CNNResidualPolicy only")
         C = model.stem[0].out_channels
@@ -169,11 +169,9 @@ class FusedRolloutForward:
         self.sample_id_base = int(sample_id_base)     # global index of row 0 (env shard offset): keys the Dropout2d stream
         self.epoch: Optional[torch.Tensor] = None     # device uint32 counter mixed into the dropout RNG (graph replays)
         self.tc_trunk = C == 96 and G == 6 and model.stem[0].in_channels <= 16 and len(model.residual_stack) >= 1
-        # Two half-batches on two streams, the second one layer behind the first and each launch capped at half the
-        # SMs: a residual-carrying layer (HBM-bound: 2.4 GB per layer at 8,192 boards) of one half then runs beside
-        # a no-residual layer (tensor-core-bound, 0.8 GB) of the other instead of each having the GPU to itself.
-        self.overlap_halves = bool(overlap_halves)
-        self._side: Optional[torch.cuda.Stream] = None
+        # grid cap of the persistent conv kernels (0 = one CTA per SM): a collector that runs two populations on two
+        # streams gives each half the SMs, so an HBM-bound residual layer of one runs beside an MMA-bound layer of the other
+        self.max_ctas = int(max_ctas)
         self._w: List = []
         self.refresh()
 
@@ -248,19 +246,16 @@ class FusedRolloutForward:
     def _drop_p(self, blk) -> float:
         return float(blk.dropout.p) if (self.model.training and isinstance(blk.dropout, torch.nn.Dropout2d)) else 0.0
 
-    def _trunk_tc(self, obs: torch.Tensor, cid: int, sample_base: Optional[int] = None, max_ctas: int = 0, after_stem=None):
-        """Medium-config shape: 11 msw_conv3x3_gn launches; returns (a16 NHWC, pooled fp32 [N, C]).
-        `after_stem` (optional callable) runs right after the stem launch (the two-stream schedule hooks in there)."""
+    def _trunk_tc(self, obs: torch.Tensor, cid: int):
+        """Medium-config shape: 11 msw_conv3x3_gn launches; returns (a16 NHWC, pooled fp32 [N, C])."""
         m = self.model
-        base = self.sample_id_base if sample_base is None else sample_base
+        base, max_ctas = self.sample_id_base, self.max_ctas
         nb, cin, hh, ww = obs.shape
         x = torch.empty((nb, 16, hh, ww), dtype=torch.float16, device=obs.device, memory_format=torch.channels_last)
         with torch.cuda.device(obs.device):
             _lib.check(_lib.load().msw_pack_obs16(obs.data_ptr(), x.data_ptr(), nb, cin, hh * ww,
                                                   torch.cuda.current_stream(obs.device).cuda_stream), "msw_pack_obs16")
         a16, a32 = conv3x3_gn(x, self.stem_taps, m.stem[1], self.stem[1], want32=True, max_ctas=max_ctas)   # stem conv + GN + ReLU
-        if after_stem is not None:
-            after_stem()
         last = len(self.blocks) - 1
         pooled = None
         for k, (blk, ((_, b1), (_, b2))) in enumerate(zip(m.residual_stack, self.blocks)):
@@ -291,28 +286,6 @@ class FusedRolloutForward:
         if not return_mine:
             return logits, value
         return logits, value, mine.reshape(n, 1, h, w)
-
-    def _call_two_streams(self, obs: torch.Tensor, return_mine: bool, cid: int):
-        dev = obs.device
-        cur = torch.cuda.current_stream(dev)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=dev)
-        side = self._side
-        n = obs.shape[0]
-        h = n // 2
-        half = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // 2)
-        stem_done = torch.cuda.Event()
-        side.wait_stream(cur)                                        # fork: obs is ready on the current stream
-        a16, pooled = self._trunk_tc(obs[:h], cid, self.sample_id_base, half, after_stem=lambda: stem_done.record(cur))
-        out0 = self._heads(a16, pooled, return_mine)
-        with torch.cuda.stream(side):
-            side.wait_event(stem_done)                               # second half runs one layer behind the first
-            b16, bpool = self._trunk_tc(obs[h:], cid, self.sample_id_base + h, half)
-            out1 = self._heads(b16, bpool, return_mine)
-        cur.wait_stream(side)                                        # join
-        for t in out1:
-            t.record_stream(cur)
-        return tuple(torch.cat((u, v), dim=0) for u, v in zip(out0, out1))
 
     def _trunk_library(self, obs: torch.Tensor, cid: int):
         """Any other shape: cuDNN fp16 NHWC convolutions with msw_gn_act between them."""
@@ -353,9 +326,6 @@ class FusedRolloutForward:
         self.calls += 1
         cid = self.calls << 8
         if (self.tc_trunk and tuple(obs.shape[2:]) == (16, 16) and obs.dtype == torch.float32 and obs.is_contiguous()):
-            n = obs.shape[0]
-            if self.overlap_halves and n % 2 == 0 and n >= 1024:
-                return self._call_two_streams(obs, return_mine, cid)
             a16, pooled = self._trunk_tc(obs, cid)
         else:
             a16, pooled = self._trunk_library(obs, cid)

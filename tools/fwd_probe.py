@@ -11,7 +11,7 @@ torch.backends.cudnn.benchmark = os.environ.get("CUDNN_BENCHMARK", "0") == "1"
 model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
                       model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).cuda()
 x = (torch.rand(N, 10, 16, 16, device="cuda") < 0.3).float()
-ff = FusedRolloutForward(model, overlap_halves=os.environ.get("OVERLAP", "1") == "1")
+ff = FusedRolloutForward(model)
 for _ in range(3):
     ff(x, return_mine=True)
 torch.cuda.synchronize()

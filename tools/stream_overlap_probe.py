@@ -5,8 +5,11 @@ Three schedules of the same rollout inner loop (forward -> masked sample -> env 
   serial      one stream, one population of 8,192 envs (what RolloutCollector does);
   env||fwd    two populations of 4,096 envs on two streams, each running its own serial loop, so one
               population's env step / sampler overlaps the other's forward (the north-star's schedule);
-  fwd halves  one population, the forward itself split into two half-batches one layer apart
-              (FusedRolloutForward(overlap_halves=True)): an HBM-bound residual layer beside an MMA-bound one.
+  capped      the same two populations with every conv launch capped at half the SMs (max_ctas = 74), so the two
+              streams run side by side instead of back to back: an HBM-bound residual layer of one population can
+              share the GPU with a tensor-core-bound layer of the other.
+(A fourth schedule -- ONE population whose forward is split into two half-batches one layer apart and re-joined
+every step -- was measured in round 2 and lost: 4.38 vs 4.04 ms per forward, the one-layer lag is paid every step.)
 Prints ms per step of 8,192 envs for each and the env-step / sampler / forward times on their own."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,9 +27,9 @@ model = m.build_model("cnn_residual", obs_shape=(10, 16, 16),
 
 
 class Pop:
-    def __init__(self, n, base, overlap):
+    def __init__(self, n, base, max_ctas):
         self.vec = m.VecMinesweeper(n, cfg, seed=0, api="torch", env_id_base=base, aux_maps=True)
-        self.fwd = FusedRolloutForward(model, overlap_halves=overlap, sample_id_base=base)
+        self.fwd = FusedRolloutForward(model, sample_id_base=base, max_ctas=max_ctas)
         self.cur, self.nxt = self.vec._alloc_encode(), self.vec._alloc_encode()
         self.a32 = torch.empty((n,), dtype=torch.int32, device=dev)
         self.r = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -55,16 +58,8 @@ def timed(fn, steps=STEPS):
     return a.elapsed_time(b) / steps
 
 
-with torch.no_grad():
-    p = Pop(N, 0, False)
-    ms_serial = timed(p.step)
-    ms_fwd = timed(lambda: p.fwd(p.cur.obs, return_mine=True))
-    lg, _, _ = p.fwd(p.cur.obs, return_mine=True)
-    ms_sample = timed(lambda: masked_sample(lg, p.cur.action_mask, seed=0, step_index=1, actions32=p.a32))
-    ms_env = timed(lambda: p.vec.step(p.a32, out=m.StepOut(obs=p.nxt.obs, action_mask=p.nxt.action_mask, rewards=p.r, dones=p.d,
-                                                           mine_labels=p.nxt.mine_labels, mine_valid=p.nxt.mine_valid), want_infos=False))
-    del p
-    pa, pb = Pop(N // 2, 0, False), Pop(N // 2, N // 2, False)
+def two_pops(max_ctas):
+    pa, pb = Pop(N // 2, 0, max_ctas), Pop(N // 2, N // 2, max_ctas)
     sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
 
     def two():
@@ -83,14 +78,25 @@ with torch.no_grad():
         two()
     sa.wait_stream(sb); e1.record(sa)
     torch.cuda.synchronize()
-    ms_two = e0.elapsed_time(e1) / STEPS
-    del pa, pb
-    ph = Pop(N, 0, True)
-    ms_halves = timed(ph.step)
-    ms_fwd_halves = timed(lambda: ph.fwd(ph.cur.obs, return_mine=True))
+    return e0.elapsed_time(e1) / STEPS
+
+
+with torch.no_grad():
+    p = Pop(N, 0, 0)
+    ms_serial = timed(p.step)
+    ms_fwd = timed(lambda: p.fwd(p.cur.obs, return_mine=True))
+    lg, _, _ = p.fwd(p.cur.obs, return_mine=True)
+    ms_sample = timed(lambda: masked_sample(lg, p.cur.action_mask, seed=0, step_index=1, actions32=p.a32))
+    ms_env = timed(lambda: p.vec.step(p.a32, out=m.StepOut(obs=p.nxt.obs, action_mask=p.nxt.action_mask, rewards=p.r, dones=p.d,
+                                                           mine_labels=p.nxt.mine_labels, mine_valid=p.nxt.mine_valid), want_infos=False))
+    ms_serial2 = timed(p.step)
+    del p
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ms_two = two_pops(0)
+    ms_cap = {c: two_pops(c) for c in (sms // 2, sms // 2 + 10, sms - 40)}
 
 print(f"components at {N} envs: forward {ms_fwd:.3f} ms, masked sampler {ms_sample * 1e3:.1f} us, env step {ms_env * 1e3:.1f} us")
-print(f"serial (one stream)                      : {ms_serial:.3f} ms / step")
+print(f"serial (one stream)                      : {ms_serial:.3f} ms / step (again after the component timings: {ms_serial2:.3f})")
 print(f"env||fwd (two populations, two streams)  : {ms_two:.3f} ms / step  ({100 * (ms_serial / ms_two - 1):+.1f} % steps/s)")
-print(f"fwd halves one layer apart (two streams) : {ms_halves:.3f} ms / step  ({100 * (ms_serial / ms_halves - 1):+.1f} % steps/s); "
-      f"forward alone {ms_fwd_halves:.3f} ms")
+for c, v in ms_cap.items():
+    print(f"capped at {c:3d} CTAs per launch            : {v:.3f} ms / step  ({100 * (ms_serial / v - 1):+.1f} % steps/s)")
