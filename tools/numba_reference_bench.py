@@ -136,7 +136,7 @@ def main():
     out["one_core_N1024_expert"] = {"env_steps_per_s": r, "board": "16x30x99", "steps": max(3, int(16 * k)), "seconds": s}
     if not a.no_fanout:
         P = len(os.sched_getaffinity(0))
-        out["fanout_P"] = fanout(a.ref_dir, 16, 16, 40, P, 256, max(4, int(24 * k)), 2)
+        out["fanout_P"] = fanout(a.ref_dir, 16, 16, 40, P, 256, max(4, int(200 * k)), 2)      # >= 1 s per worker
         out["fanout_P"]["board"] = "16x16x40"
     print(json.dumps(out))
 
