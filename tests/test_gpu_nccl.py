@@ -60,7 +60,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 8])
 def test_flat_grad_allreduce_nccl(world, tmp_path):
     import torch
     if torch.cuda.device_count() < world:
