@@ -530,12 +530,14 @@ class VecMinesweeper:
         n = self.num_envs
         pin, st = self._host_buffers()
         ap = actions_pinned.data_ptr()
-        if ap not in self._pinned_ok:                          # is_pinned() is a driver query: ask once per buffer
-            if not (actions_pinned.dtype == torch.int32 and actions_pinned.is_pinned() and
-                    tuple(actions_pinned.shape) == (n,) and actions_pinned.is_contiguous()):
+        if ap not in self._pinned_ok:                          # is_pinned() is a driver query: ask once per ALLOCATION
+            base = actions_pinned.untyped_storage().data_ptr()
+            if not (actions_pinned.dtype == torch.int32 and tuple(actions_pinned.shape) == (n,) and
+                    actions_pinned.is_contiguous() and (base in self._pinned_ok or actions_pinned.is_pinned())):
                 raise ValueError("step_host: actions must be a pinned contiguous int32 [num_envs] CPU tensor")
             if len(self._pinned_ok) < 65536:
                 self._pinned_ok.add(ap)
+                self._pinned_ok.add(base)
         key = (copy_obs, copy_infos, self.aux_maps)
         prepared = self._host_calls.get(key)
         if prepared is None:                                   # struct filling is per-configuration, not per step

@@ -131,3 +131,77 @@ def test_unmodified_evaluate_vec_on_cuda_env():
     assert want2["avg_steps"] > 3.0
     print("C1 (random-init medium policy):", got)
     print("C1 (scripted policy):", got2)
+
+
+def test_live_collect_rollout_buffer_and_gae():
+    """The reference's REAL collector (train_rl.collect_rollout, train_rl.py:155-289) run live on this box --
+    reference numba env on the host, the reference's medium cnn_residual on the GPU under fp16 autocast, torch's
+    Categorical sampling, aux maps on -- at 1,024 envs x 64 steps, then RolloutBuffer.compute_gae on the GPU with
+    the fp16 bootstrap value autocast produces (train_rl.py:272-277).  The CUDA env, fed the same actions and the
+    reference's mine layouts through the direct-write buffer protocol (slot t+1 gets obs / mask / labels / valid,
+    slot t gets reward / done), must rebuild the reference's buffer bit for bit, and msw_gae must reproduce its
+    advantages / returns bit for bit from the reference's values."""
+    import torch
+    import minesweeper_ppo_b200 as m
+    RL.require()
+    mods = RL.load()
+    import importlib
+    train_rl = importlib.import_module("train_rl")
+    E = mods["env"]
+    N, T, H, W = 1024, 64, 16, 16
+    HW = H * W
+    cfg = E.EnvConfig(H=H, W=W, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    torch.manual_seed(0)
+    model = mods["models"].build_model("cnn_residual", obs_shape=(10, H, W),
+                                       model_cfg=dict(stem_channels=96, blocks=5, dropout=0.05, value_hidden=256)).cuda()
+    dev = torch.device("cuda")
+    with RL.LayoutRecorder() as rec:
+        vec = E.VecMinesweeper(N, cfg, seed=21)
+        index_of = {id(e): i for i, e in enumerate(vec.envs)}
+        placed = []                       # (step, env, layout)
+        tcount = [0]
+        orig_step = vec.step
+
+        def step_logged(actions):
+            r = orig_step(actions)
+            for i, mm in rec.drain(index_of):
+                placed.append((tcount[0], i, mm.reshape(-1)))
+            tcount[0] += 1
+            return r
+
+        vec.step = step_logged
+        buf, aux = train_rl.collect_rollout(vec, model, T, dev, aux_mine_weight=0.05, aux_mine_calib_weight=0.01)
+    last_values = aux["last_values"].detach()
+    assert last_values.dtype == torch.float16, "autocast bootstrap value (train_rl.py:272-277)"
+    buf.compute_gae(last_values, gamma=0.995, lam=0.95)
+    assert int(buf.dones.sum()) > 1000 and len(placed) > 1000
+
+    v = m.VecMinesweeper(N, m.EnvConfig(H=H, W=W, mine_count=40, step_penalty=1e-4), api="torch", aux_maps=True)
+    mine = m.RolloutBuffer(N, T, (10, H, W), HW, v.device, aux_maps=True)
+    scratch = v._alloc_encode()
+    v.reset(out=mine.slot(0))
+    by_step = {}
+    for t, i, mm in placed:
+        by_step.setdefault(t, []).append((i, mm))
+    ref_actions = buf.actions.view(T, N)
+    for t in range(T):
+        sel = np.zeros(N, bool)
+        lay = np.zeros((N, HW), bool)
+        for i, mm in by_step.get(t, ()):
+            sel[i], lay[i] = True, mm
+        v.inject_layouts(lay, sel)
+        nxt = mine.slot(t + 1) if t + 1 < T else scratch
+        cur = mine.slot(t)
+        v.step(ref_actions[t].to(v.device), out=m.StepOut(obs=nxt.obs, action_mask=nxt.action_mask, rewards=cur.rewards,
+                                                          dones=cur.dones, mine_labels=nxt.mine_labels,
+                                                          mine_valid=nxt.mine_valid), want_infos=False)
+    mine.values.copy_(buf.values)
+    mine.compute_gae(last_values, 0.995, 0.95)
+    torch.cuda.synchronize()
+    for name in ("obs", "action_mask", "rewards", "dones", "mine_labels", "mine_valid", "advantages", "returns"):
+        a, b = getattr(mine, name), getattr(buf, name)
+        assert a.dtype == b.dtype and a.shape == b.shape, name
+        if a.dtype.is_floating_point:
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), name      # bit patterns
+        else:
+            assert torch.equal(a, b), name
