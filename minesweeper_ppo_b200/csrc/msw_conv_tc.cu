@@ -30,6 +30,13 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+// Ablation switches for tools/convgn_ablation.py: compiled in only with -DMSW_DEV_KNOBS (the product library has none).
+#ifdef MSW_DEV_KNOBS
+#define MSW_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define MSW_DBG(bit) false
+#endif
+
 namespace msw {
 
 namespace cv {
@@ -234,6 +241,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned a0 = base + OFF_A + s * A_STAGE, a1 = a0 + A0_BYTES, d = tmem + acc * C;
             unsigned accumulate = 0u;
+            if (!MSW_DBG(8))
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -283,7 +291,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) cv_bar_arrive(tempty(acc));       // the accumulator is in registers: release it
-            if (dbg & 1) continue;
+            if (MSW_DBG(1)) continue;
             __half *dst = out + (board * 256 + (it & 1u) * 128 + q * 32 + lane) * (long long)C + third * 32;
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -344,6 +352,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) cv_bar_arrive(tempty(acc));
+                if (MSW_DBG(16)) continue;
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     const uint32_t *src = jj < 8 ? lo : hi;
@@ -364,6 +373,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     }
                 }
             }
+            if (MSW_DBG(16)) continue;
             // the warp's (mean, M2) over its 1,024 values per group; the board's statistics are merged from the four
             // row-owning warps of a channel third in a fixed order (Chan et al.)
             s1a = cv_warp_sum(s1a); s2a = cv_warp_sum(s2a);
@@ -373,7 +383,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 dst[0] = shift0 + s1a * (1.0f / 1024.0f); dst[1] = s2a - s1a * s1a * (1.0f / 1024.0f);
                 dst[2] = shift1 + s1b * (1.0f / 1024.0f); dst[3] = s2b - s1b * s1b * (1.0f / 1024.0f);
             }
-            asm volatile("bar.sync 1, 384;" ::: "memory");
+            if (!MSW_DBG(2)) asm volatile("bar.sync 1, 384;" ::: "memory");
             if (te < C) {
                 // one thread per channel folds statistics, affine, conv bias and the Dropout2d scale into y = a*x + b
                 const int c = te, gsel = (c >> 4) & 1, w4 = (c >> 5) * 4;
@@ -391,7 +401,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 s_ab[(par * 2 + 0) * C + c] = a * sc;
                 s_ab[(par * 2 + 1) * C + c] = fmaf(s_cb[c] - mg, a, gp.beta[c]) * sc;
             }
-            asm volatile("bar.sync 1, 384;" ::: "memory");
+            if (!MSW_DBG(2)) asm volatile("bar.sync 1, 384;" ::: "memory");
             // ---- normalise, (+ residual), ReLU, store: chunk by chunk (8 channels), both tiles per chunk
             const float4 *a4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 0) * C + cbase);
             const float4 *b4 = reinterpret_cast<const float4 *>(s_ab + (par * 2 + 1) * C + cbase);
@@ -427,7 +437,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                             ps[j + 1] = half == 0 ? v1 : ps[j + 1] + v1;
                         }
                     }
-                    if (EPI != 2 && gp.y32) cv_st256(gp.y32 + cv_p8(board, half, third, c0 >> 3, pp), o);
+                    if (EPI != 2 && gp.y32 && !MSW_DBG(1)) cv_st256(gp.y32 + cv_p8(board, half, third, c0 >> 3, pp), o);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1]));
@@ -460,7 +470,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     uint32_t packed[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) packed[k] = h[half][(c0 >> 1) + k];
-                    cv_st256(out + px * C + cbase + c0, packed);
+                    if (!MSW_DBG(1)) cv_st256(out + px * C + cbase + c0, packed);
                 }
             }
         }
@@ -559,7 +569,12 @@ static int conv_launch(const char *who, const void *x16, const void *w_taps16, v
         if (r0 != CUDA_SUCCESS || (Cin == 96 && r1 != CUDA_SUCCESS))
             return fail(MSW_ERR_ARG, "%s: weight tensor map failed (%d, %d)", who, (int)r0, (int)r1);
     }
-    const int dbg = 0;      // (bit 0 skips the plain epilogue's stores: used once to time the MMA + TMA part alone)
+#ifdef MSW_DEV_KNOBS
+    const char *dbg_env = getenv("MSW_CONV_DBG");          // tools/convgn_ablation.py only
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+    const int dbg = 0;
+#endif
     const ConvGnParams none = {};
     const ConvGnParams &gp = gn ? *gn : none;
     cudaStream_t st = (cudaStream_t)stream;
