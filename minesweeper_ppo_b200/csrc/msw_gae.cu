@@ -177,6 +177,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
                  :: "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one()      // one lane of a converged warp (elect.sync)
+{
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0u;
+}
+
 __global__ void __launch_bounds__(TG_THREADS)
 gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_constant__ CUtensorMap m_values,
                const __grid_constant__ CUtensorMap m_dones, const __grid_constant__ CUtensorMap m_adv,
@@ -206,7 +213,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_const
     for (long long k = tiles - 1; k >= 0; --k, parity ^= 1u) {
         const int row0 = (int)(k * TG_ROWS);
         const int rows = (int)(T - row0 < TG_ROWS ? T - row0 : TG_ROWS);
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {         // elect.sync: the TMA instructions issue without a divergence waterfall
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&S.bar)), "r"(TILE_BYTES) : "memory");
             tma_load_2d(&S.r[0][0], &m_rewards, col0, row0, &S.bar);
             tma_load_2d(&S.v[0][0], &m_values, col0, row0, &S.bar);
@@ -255,7 +262,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_const
         for (int i = warp; i < rows; i += TG_THREADS / 32) S.v[i][lane] = __fadd_rn(S.r[i][lane], S.v[i][lane]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA store
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tma_store_2d(&m_adv, col0, row0, &S.r[0][0]);
             tma_store_2d(&m_ret, col0, row0, &S.v[0][0]);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -263,7 +270,7 @@ gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_const
         }
         if (k > 0) __syncthreads();
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)

@@ -78,6 +78,14 @@ __device__ __forceinline__ void tc_commit(unsigned bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
+// One lane of a converged warp: inside an elect.sync region ptxas issues tcgen05 / TMA instructions without the
+// divergence waterfall it wraps around them under `lane == 0` (see msw_conv_tc.cu).
+__device__ __forceinline__ bool tc_elect_one()
+{
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void tc_ld32(unsigned taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,7 +140,8 @@ heads_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = *s_tmem;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+        if (tc_elect_one()) {
         // ---- TMA producer
         tc_bar_expect(bfull, Cfg::B_BYTES);
         for (int kb = 0; kb < Cfg::KB; ++kb) tc_tma_load(sB + kb * Cfg::B_BLOCK, &map_w, kb * 64, 0, bfull);
@@ -144,7 +153,8 @@ heads_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int kb = 0; kb < Cfg::KB; ++kb)
                 tc_tma_load(sA + s * Cfg::A_STAGE + kb * Cfg::A_BLOCK, &map_a, kb * 64, (int)(tile * TC_ROWS), full(s));
         }
-    } else if (warp == 1 && lane == 0) {
+        }
+    } else if (warp == 1) {
         // ---- MMA issuer.  Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major (0),
         // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
         constexpr unsigned idesc = (1u << 4) | ((unsigned)(Cfg::N >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
@@ -156,6 +166,7 @@ heads_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tc_bar_wait(full(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned d = tmem + as * TC_ACC_STRIDE;
+            if (tc_elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
                 const int kb = ks / 4, k = ks % 4;                          // 4 k-steps of 32 bytes per swizzle atom
@@ -165,6 +176,8 @@ heads_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             tc_commit(empty(s));             // the smem stage is free once these MMAs have read it
             tc_commit(tfull(as));            // ... and the accumulator is complete
+            }
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---- epilogue: thread = one row of the tile (TMEM lane), one head per warpgroup

@@ -3,6 +3,7 @@ switched off through the -DMSW_DEV_KNOBS build (tools/_dev/libmsw_b200_dev.so, b
 minesweeper_ppo_b200.build.build_dev); results are wrong by construction, only the times matter.
   0   everything on                      1  no global stores            2  no statistics barriers
   8   no MMAs (TMA + epilogue only)      16 epilogue = tcgen05.ld + release only (TMA + MMA only)
+  32  no horizontal tap shift (every A descriptor atom-aligned)        64 no disable-output-lane masks
 Each variant runs in its own process (MSW_CONV_DBG is read at launch time by the dev library)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,7 +41,12 @@ if __name__ == "__main__":
         from minesweeper_ppo_b200 import build as b
         os.makedirs(os.path.dirname(DEV), exist_ok=True)
         b.build_dev(DEV)
-    for dbg in (0, 1, 2, 3, 8, 9, 16, 24):
-        env = dict(os.environ, MSW_CONV_DBG=str(dbg))
-        r = subprocess.run([sys.executable, "-c", CHILD], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-        print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"dbg={dbg}: no output", flush=True)
+    for pair in (0, 1):
+        for dbg in ((0, 1, 16) if "--quick" in sys.argv else (0, 1, 2, 3, 8, 9, 16, 24, 48, 80, 112)):
+            env = dict(os.environ, MSW_CONV_DBG=str(dbg), MSW_CONV_PAIR=str(pair))
+            try:
+                r = subprocess.run([sys.executable, "-c", CHILD], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+                out = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "no output"
+            except subprocess.TimeoutExpired:
+                out = "TIMEOUT (hang)"
+            print(f"pair={pair} {out}", flush=True)
