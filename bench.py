@@ -315,8 +315,9 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     del actions_log
     torch.cuda.empty_cache()
 
-    def run_host(copy_obs: bool, steps: int):
+    def run_host(copy_obs: bool, steps: int, delta: bool = True):
         v = make_env()
+        v.host_delta = delta
         v.reset()
         for t in range(Wm):
             v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
@@ -335,16 +336,19 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         return max(e0.elapsed_time(e1) / 1e3, wall), wall, done_count
 
     if args.no_e2e:
-        Kh = 1
-        e2e_s, e2e_full_s, episodes = float("inf"), float("inf"), None
+        Kh = Kf = 1
+        e2e_s, e2e_full_s, e2e_rewrite_s, episodes = float("inf"), float("inf"), float("inf"), None
     else:
         e2e_s, e2e_wall, episodes = run_host(False, Ke)
-        Kh = min(Ke, 12)
+        Kh = Ke
         e2e_full_s, _, _ = run_host(True, Kh)
+        Kf = min(Ke, 12)
+        e2e_rewrite_s, _, _ = run_host(True, Kf, delta=False)
 
     ms_total_max = reduce_max(ms_total)
     e2e_s_max = reduce_max(e2e_s)
     e2e_full_max = reduce_max(e2e_full_s)
+    e2e_rewrite_max = reduce_max(e2e_rewrite_s)
     kernel_ms_ranks = gather(ms_kernel)
     ms_kernel_max = max(kernel_ms_ranks)
     del acts_host
@@ -392,9 +396,13 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
             "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": host_obs_d2h_bytes(m, N),
             "call": "same call with copy_obs=True: the full reference-shaped NumPy result (obs fp32 [N,10,H,W] + mask + "
                     "reward + done) in host memory every step.  The planes do not cross PCIe: msw_step_host copies the "
-                    "packed post-step state (85 B/env) and expands it on all host threads with non-temporal stores "
-                    "(msw_host_expand.cu); the call is bound by host memory store bandwidth "
-                    f"({(41 * H * W) * N / 1e6:.0f} MB written per step)",
+                    "packed post-step state (85 B/env) and expands it on all host threads (msw_host_expand.cpp).  The "
+                    "result arrays are recycled (two sets alternate here, as in any loop that keeps the previous batch) "
+                    "and each carries a shadow of the bit planes it holds, so only the cache lines that changed since "
+                    "the set was last filled are rewritten (non-temporal stores)",
+            "full_rewrite": {"value": total_envs * Kf / e2e_rewrite_max, "steps": Kf,
+                             "note": f"host_delta=False: every byte of obs/mask rewritten each step "
+                                     f"({(41 * H * W) * N / 1e6:.0f} MB, bound by host store bandwidth)"},
             "host_threads": host_threads(),
         },
         "gpu_launches": K,

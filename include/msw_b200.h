@@ -332,7 +332,9 @@ typedef struct msw_host_out {
     int32_t *revealed_count;       /* nullable */
     int32_t *stage;                /* pinned, required when obs or mask is set */
     int32_t  threads;
-    int32_t  reserved;
+    int32_t  shadow_valid;         /* 0: obs / mask hold anything -> everything is written and the shadow initialised;
+                                    * != 0: obs / mask hold exactly what `shadow` describes -> only what differs is rewritten */
+    uint64_t *shadow;              /* nullable; [n][msw_shadow_words(H, W)] ordinary host memory (see below) */
 } msw_host_out;
 
 /* The host-side expansion on its own: packed state arrays IN HOST MEMORY (h_mines / h_revealed int32 [n][wpb],
@@ -341,6 +343,17 @@ typedef struct msw_host_out {
  * VecMinesweeper.reset() in the NumPy convention. */
 int msw_expand_obs_host(const msw_env_desc *desc, const int32_t *h_mines, const int32_t *h_revealed,
                         const int32_t *h_meta, int64_t n, float *h_obs, uint8_t *h_mask, int32_t threads);
+
+/* Delta mode of the expansion.  A caller that keeps the SAME obs / mask arrays across calls (the Python mirror
+ * recycles them from a pool, VecMinesweeper._result_arrays) passes a `shadow`: the 10*H*W bit planes those arrays
+ * currently hold (bit p*HW + r*W + c of env i's msw_shadow_words(H, W) little-endian 64-bit words = obs[i][p][r][c],
+ * plane 0 = ~mask).  Only the groups of eight values whose bits differ from the shadow are rewritten (a step changes
+ * ~10 % of an env's cache lines under random play), then the shadow is updated; the arrays end up byte-identical to
+ * the full expansion as long as nobody else wrote to them.  obs, mask and shadow are all required. */
+int msw_shadow_words(int32_t H, int32_t W);     /* 64-bit words per env; 0 for an unsupported board */
+int msw_expand_obs_host_delta(const msw_env_desc *desc, const int32_t *h_mines, const int32_t *h_revealed,
+                              const int32_t *h_meta, int64_t n, float *h_obs, uint8_t *h_mask,
+                              uint64_t *shadow, int32_t shadow_valid, int32_t threads);
 
 int msw_step_host(const msw_env_desc *desc, const msw_state *st,
                   const msw_step_io *io, const int32_t *h_actions32,

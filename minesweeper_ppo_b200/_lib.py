@@ -45,7 +45,7 @@ class HostOut(C.Structure):          # msw_host_out
     _fields_ = [
         ("obs", C.c_void_p), ("mask", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("outcome", C.c_void_p), ("new_reveals", C.c_void_p), ("step", C.c_void_p), ("revealed_count", C.c_void_p),
-        ("stage", C.c_void_p), ("threads", C.c_int32), ("reserved", C.c_int32),
+        ("stage", C.c_void_p), ("threads", C.c_int32), ("shadow_valid", C.c_int32), ("shadow", C.c_void_p),
     ]
 
 
@@ -65,6 +65,9 @@ SIGNATURES = {
     "msw_step_host": (C.c_int, [_P(EnvDesc), _P(State), _P(StepIO), C.c_void_p, _P(HostOut), C.c_int64, C.c_void_p]),
     "msw_expand_obs_host": (C.c_int, [_P(EnvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_int32]),
+    "msw_shadow_words": (C.c_int, [C.c_int32, C.c_int32]),
+    "msw_expand_obs_host_delta": (C.c_int, [_P(EnvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_int32]),
     "msw_masked_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                                     C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msw_gn_act": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,

@@ -22,9 +22,9 @@
 
 namespace msw {
 
-// msw_host_expand.cu: packed state -> the reference's fp32 observation planes / bool mask, on host threads
+// msw_host_expand.cpp: packed state -> the reference's fp32 observation planes / bool mask, on host threads
 void expand_obs_host(int H, int W, const uint32_t *mines, const uint32_t *revealed, const int32_t *meta, long long n,
-                     float *obs, uint8_t *mask, int threads);
+                     float *obs, uint8_t *mask, uint64_t *shadow, int shadow_valid, int threads);
 
 struct EnvParams {
     int H, W, HW, wpb;
@@ -1031,6 +1031,8 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     const size_t wpb = (size_t)p.wpb;
     if (expand) {
         if (!h->stage) return fail(MSW_ERR_NULL, "msw_step_host: host obs/mask requested without the pinned state staging area");
+        if (h->shadow && !(h->obs && h->mask))
+            return fail(MSW_ERR_NULL, "msw_step_host: a shadow describes BOTH result arrays: obs and mask are required with it");
         d2h(h->stage, st->mines, N * wpb * 4);
         d2h(h->stage + N * wpb, st->revealed, N * wpb * 4);
         d2h(h->stage + 2 * N * wpb, st->meta, N * 16);
@@ -1052,7 +1054,7 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     MSW_CUDA_TRY(cudaStreamSynchronize(s));
     if (expand)
         expand_obs_host(p.H, p.W, reinterpret_cast<const uint32_t *>(h->stage), reinterpret_cast<const uint32_t *>(h->stage + N * wpb),
-                        h->stage + 2 * N * wpb, (long long)n, h->obs, h->mask, h->threads);
+                        h->stage + 2 * N * wpb, (long long)n, h->obs, h->mask, h->shadow, h->shadow_valid, h->threads);
     return MSW_OK;
 }
 

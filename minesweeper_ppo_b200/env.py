@@ -136,6 +136,21 @@ class _EnvList:
         return (self[i] for i in range(len(self)))
 
 
+class _ResultSet:
+    """One recycled (obs, mask) pair of the NumPy calling convention with the shadow msw_step_host's delta
+    expansion keeps for it.  obs is 64-byte aligned (one board row of a 16-wide plane = one cache line)."""
+    __slots__ = ("raw", "obs", "mask", "shadow", "valid")
+
+    def __init__(self, n: int, H: int, W: int, shadow_words: int):
+        count = n * OBS_CHANNELS * H * W
+        self.raw = np.empty((count + 16,), np.float32)
+        off = ((-self.raw.ctypes.data) % 64) // 4
+        self.obs = self.raw[off:off + count].reshape(n, OBS_CHANNELS, H, W)
+        self.mask = np.empty((n, H * W), bool)
+        self.shadow = np.empty((n, max(1, shadow_words)), np.uint64)
+        self.valid = 0                     # 0: obs / mask hold garbage; 1: exactly what `shadow` describes
+
+
 class VecMinesweeper:
     """Batched Minesweeper on one B200; API of the reference class (env.py:379-517)."""
 
@@ -195,6 +210,7 @@ class VecMinesweeper:
         self._host_calls: Dict[Any, Any] = {}
         self._pinned_ok: set = set()
         self._result_pool: list = []
+        self.host_delta = True       # NumPy convention: rewrite only what changed in a recycled result set (step_host)
         self._staging: Dict[str, torch.Tensor] = {}
         # late-start curriculum (env.py:397-403, 416-466): parameters normalised as the reference does
         self._late = None
@@ -505,20 +521,22 @@ class VecMinesweeper:
         wpb = (H * W + 31) // 32
         return n * ((2 * wpb + 4) * 4 + 5)
 
-    def _result_arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+    def _result_arrays(self) -> "_ResultSet":
         """(obs f32 [n,10,H,W], mask bool [n,HW]) for the next result.  The reference returns fresh arrays every
         call (np.stack, env.py:507-510); fresh 688 MB allocations would cost more in page faults than the whole
         step, so arrays are recycled from a small pool -- but ONLY when nobody else references them any more
-        (any view / torch.from_numpy alias keeps a reference to its base array), otherwise a new one is made."""
+        (any view / torch.from_numpy alias keeps a reference to the array or to its base), otherwise a new set is
+        made.  A pooled set carries a `shadow` (the bit planes the arrays hold, include/msw_b200.h), so
+        msw_step_host rewrites only the cache lines that changed since the set was last filled."""
         import sys
-        for k, (o, m) in enumerate(self._result_pool):
-            if sys.getrefcount(o) <= 3 and sys.getrefcount(m) <= 3:      # pool tuple + loop variable + getrefcount argument
-                return o, m
-        o = np.empty((self.num_envs, OBS_CHANNELS, self.H, self.W), np.float32)
-        m = np.empty((self.num_envs, self.HW), bool)
+        for e in self._result_pool:
+            # e.obs: slot + argument; e.raw: slot + obs.base + argument; e.mask: slot + argument
+            if sys.getrefcount(e.obs) <= 2 and sys.getrefcount(e.raw) <= 3 and sys.getrefcount(e.mask) <= 2:
+                return e
+        e = _ResultSet(self.num_envs, self.H, self.W, self._L.msw_shadow_words(self.H, self.W))
         if len(self._result_pool) < 4:
-            self._result_pool.append((o, m))
-        return o, m
+            self._result_pool.append(e)
+        return e
 
     def step_host(self, actions_pinned: torch.Tensor, *, copy_obs: bool = True, copy_infos: bool = True,
                   out: Optional[Tuple[np.ndarray, np.ndarray]] = None, threads: int = 0) -> Dict[str, Any]:
@@ -573,8 +591,13 @@ class VecMinesweeper:
         res: Dict[str, Any] = dict(pin)
         if not copy_obs:
             res["obs_device"], res["mask_device"] = st["h_obs"], st["h_mask"]
+        rset = None
         if copy_obs:
-            obs, mask = out if out is not None else self._result_arrays()
+            if out is not None:
+                obs, mask = out
+            else:
+                rset = self._result_arrays()
+                obs, mask = rset.obs, rset.mask
             if (obs.dtype != np.float32 or obs.shape != (n, OBS_CHANNELS, self.H, self.W) or not obs.flags.c_contiguous
                     or mask.dtype != np.bool_ or mask.shape != (n, self.HW) or not mask.flags.c_contiguous):
                 raise ValueError("step_host: out must be (float32 [n,10,H,W], bool [n,HW]) C-contiguous arrays")
@@ -582,6 +605,11 @@ class VecMinesweeper:
             res["obs"], res["mask"] = obs, mask
         else:
             h.obs = h.mask = None
+        if rset is not None and self.host_delta:               # delta mode: only what changed since this set was filled
+            h.shadow, h.shadow_valid = rset.shadow.ctypes.data, rset.valid
+            rset.valid = 0                                     # until the call has succeeded
+        else:
+            h.shadow, h.shadow_valid = None, 0
         h.threads = int(threads)
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
@@ -592,6 +620,8 @@ class VecMinesweeper:
                 rc = self._L.msw_step_host(r_desc, r_state, r_io, ap, r_h, n, self._stream())
         if rc:
             _lib.check(rc, "msw_step_host")
+        if rset is not None:
+            rset.valid = 1
         self._inject = None
         self._cache = None
         if self.aux_maps:

@@ -81,6 +81,6 @@ def test_product_never_imports_oracle():
     banned = re.compile(r"import\s+oracle|from\s+oracle|oracle\.|oracle/|libmsw_oracle|msw_oracle|\borc_[a-z]")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 hit = banned.search(open(os.path.join(dp, f)).read())
                 assert hit is None, (f, hit.group(0))

@@ -56,6 +56,52 @@ def test_numpy_api_is_reference_shaped(torch_cuda):
             assert not e.flags.any() and e.H == 16 and e.W == 16
 
 
+@pytest.mark.parametrize("H,W,M", [(16, 16, 40), (16, 30, 99), (9, 9, 10)])
+def test_numpy_api_recycled_result_arrays(torch_cuda, oracle, H, W, M):
+    """The NumPy convention recycles its result arrays and rewrites only what changed since a set was last filled
+    (msw_host_out.shadow).  Whatever the caller does with earlier results -- drops them at once (one set reused
+    every step), keeps the previous batch (two sets alternate), keeps views alive for a while (more sets, stale by
+    several steps), or passes its own `out` arrays -- every result equals the oracle's, and results the caller
+    still holds are never written to."""
+    import os
+    import minesweeper_ppo_b200 as m
+    N, HW = 333, H * W
+    cfg = m.EnvConfig(H=H, W=W, mine_count=M, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    v = m.VecMinesweeper(N, cfg, seed=11)
+    cpu = oracle.OracleVecEnv(N, cfg, seed=11, nthreads=os.cpu_count() or 1)
+    rng = np.random.default_rng(3)
+    batch = v.reset()
+    b = cpu.reset()
+    P.assert_bits_equal(batch["obs"], b["obs"], "reset obs")
+    held = []                                                   # (release step, view, snapshot)
+    for t in range(48):
+        sc = rng.random((N, HW))
+        sc[~b["action_mask"]] = -1
+        a = sc.argmax(1) if t % 6 != 5 else rng.integers(0, HW, size=N)
+        phase = t // 12
+        if phase == 0:
+            batch = None                                        # nothing referenced: one set, one step stale
+        if phase == 2 and t % 3 == 0:
+            held.append((t + 4, batch["obs"][5:9], batch["obs"][5:9].copy()))      # a VIEW keeps the set out of the pool
+        if phase == 3 and t % 2 == 0:
+            own = (np.full((N, 10, H, W), np.nan, np.float32), np.zeros((N, HW), bool))
+            pin = v._host_buffers()[0]
+            pin["actions"].numpy()[:] = a
+            res = v.step_host(pin["actions"], out=own)
+            batch = {"obs": res["obs"], "action_mask": res["mask"]}
+            assert batch["obs"] is own[0]
+        else:
+            batch, _, _, _ = v.step(a)
+        b, _, _, _ = cpu.step(a, tensor_infos=True)
+        P.assert_bits_equal(batch["obs"], b["obs"], f"t={t} obs")
+        P.assert_bits_equal(batch["action_mask"], b["action_mask"], f"t={t} mask")
+        for rel, view, snap in held:
+            assert np.array_equal(view, snap), f"a held result was overwritten at t={t}"
+        held = [h for h in held if h[0] > t]
+    assert len(v._result_pool) >= 2 and all(e.valid for e in v._result_pool)
+    assert int(cpu.episode_idx.max()) > 1
+
+
 def test_cuda_floodfill_with_flags_matches_numba(torch_cuda):
     """Arbitrary (mines, revealed, flags, start) boards, including flags the hot path never sets."""
     import minesweeper_ppo_b200 as m

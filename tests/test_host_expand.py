@@ -66,3 +66,64 @@ def test_expand_unaligned_and_partial_outputs(oracle):
     mask = np.zeros((N, HW), bool)
     assert L.msw_expand_obs_host(C.byref(desc), pm.ctypes.data, pr.ctypes.data, meta.ctypes.data, N, None, mask.ctypes.data, 0) == 0
     assert np.array_equal(mask, ~rev)
+
+
+@pytest.mark.parametrize("H,W,M", [(16, 16, 40), (16, 30, 99), (30, 16, 99), (8, 8, 10), (5, 7, 6), (1, 9, 2), (3, 32, 20),
+                                   (31, 31, 120)])
+@pytest.mark.parametrize("sets,threads,align", [(1, 1, 64), (2, 5, 64), (2, 3, 4)])
+def test_delta_expansion_tracks_a_trajectory(oracle, H, W, M, sets, threads, align):
+    """msw_expand_obs_host_delta over a played trajectory (opened boards, no-op clicks, auto-resets): `sets` result
+    array pairs are used round-robin as VecMinesweeper's pool does (so a pair is `sets` steps stale when it is
+    reused), each with its own shadow; after every call the arrays equal the oracle's encoder bit for bit."""
+    from minesweeper_ppo_b200 import _lib
+    L = _lib.load()
+    O = oracle
+    N, HW = 257, H * W
+    SW = L.msw_shadow_words(H, W)
+    assert SW == (10 * HW + 63) // 64 + 1
+    cfg = O.OracleEnvConfig(H=H, W=W, mine_count=M, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    vec = O.OracleVecEnv(N, cfg, seed=5, nthreads=2)
+    rng = np.random.default_rng(H * 1000 + W + sets)
+    desc = _lib.EnvDesc(H, W, M, 1, 0.0, 0.0, 0.0, 0, 0, 0)
+    pool = []
+    for s in range(sets):
+        raw = np.full(N * 10 * HW + 32, np.nan, np.float32)                       # garbage before the first call
+        off = ((-raw.ctypes.data) % 64) // 4 + (0 if align == 64 else 1)          # 64-byte aligned or only 4-byte aligned
+        obs = raw[off:off + N * 10 * HW].reshape(N, 10, H, W)
+        mask = np.ones((N, HW), bool) if s else np.zeros((N, HW), bool)
+        pool.append([obs, mask, np.full((N, SW), 0x5555555555555555, np.uint64), 0, raw])
+    b = vec.reset()
+    for t in range(14):
+        if t % 5 == 4:                                                         # any cell: includes no-op clicks
+            a = rng.integers(0, HW, size=N)
+        else:
+            s_ = rng.random(b["action_mask"].shape)
+            s_[~b["action_mask"]] = -1
+            a = s_.argmax(1)
+        b, _, _, _ = vec.step(a, tensor_infos=True)
+        mines, rev = _pack(vec.mine.astype(bool), HW), _pack(vec.revealed.astype(bool), HW)
+        meta = np.zeros((N, 4), np.int32)
+        meta[:, 0] = vec.first_click_done
+        e = pool[t % sets]
+        rc = L.msw_expand_obs_host_delta(C.byref(desc), mines.ctypes.data, rev.ctypes.data, meta.ctypes.data, N,
+                                         e[0].ctypes.data, e[1].ctypes.data, e[2].ctypes.data, e[3], threads)
+        assert rc == 0
+        e[3] = 1
+        assert np.array_equal(e[0].view(np.uint32), b["obs"].view(np.uint32)), (H, W, t)
+        assert np.array_equal(e[1], b["action_mask"]), (H, W, t)
+        # the shadow is the bit string of the arrays: plane 0 = revealed
+        bits = np.unpackbits(e[2].view(np.uint8), axis=1, bitorder="little")[:, :10 * HW]
+        assert np.array_equal(bits.astype(bool), b["obs"].reshape(N, -1) != 0)
+
+
+def test_delta_expansion_requires_both_arrays(oracle):
+    from minesweeper_ppo_b200 import _lib
+    L = _lib.load()
+    desc = _lib.EnvDesc(16, 16, 40, 1, 0.0, 0.0, 0.0, 0, 0, 0)
+    z = np.zeros((4, 8), np.int32)
+    meta = np.zeros((4, 4), np.int32)
+    sh = np.zeros((4, 41), np.uint64)
+    obs = np.zeros((4, 10, 16, 16), np.float32)
+    assert L.msw_expand_obs_host_delta(C.byref(desc), z.ctypes.data, z.ctypes.data, meta.ctypes.data, 4, obs.ctypes.data,
+                                       None, sh.ctypes.data, 0, 1) != 0
+    assert b"shadow" in L.msw_last_error()
