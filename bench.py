@@ -37,6 +37,11 @@ ENVS_PER_GPU = 65536
 BYTES_PER_STEP = 41 * H * W + 9          # 10,505 B
 WORKLOAD = "C2"
 VALID_ONLY = True
+# Workload setup, both arms: reset() starts every env's first episode at the same instant, so the first ~20 steps are
+# not random play in steady state (every env opens its first region together, then the first wave of losses ...).
+# PRE_ROLL untimed env steps after reset() bring the batch to the stationary mix of episode phases (episodes last
+# ~5.6 steps under random play) before the W warm-up and K timed steps.
+PRE_ROLL = 32
 
 
 def set_workload(name: str, envs):
@@ -64,7 +69,7 @@ def bench_config(world: int) -> dict:
         "envs_total": ENVS_PER_GPU * world,
         "actions": ("uniform random valid cell" if VALID_ONLY else "uniform random cell (series B, no-op clicks included)")
                    + " per env per step",
-        "auto_reset": True, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
+        "auto_reset": True, "pre_roll_steps": PRE_ROLL, "obs_layout": f"fp32 [N,10,{H},{W}] + bool mask [N,{H * W}] (reference layout)",
         "l2": f"each step writes {BYTES_PER_STEP * ENVS_PER_GPU / 1e6:.0f} MB of obs/mask (>> 126 MB L2), no explicit flush",
         "parallelism": f"env shards, {world} rank(s), no data-path collective",
     }
@@ -184,6 +189,7 @@ def cpu_env_steps_per_s(n_envs: int, steps: int, warmup: int, threads: int):
     mask = vec.reset()["action_mask"]
     total = 0.0
     per_step = []
+    warmup += PRE_ROLL                     # untimed: pre-roll to the stationary episode mix, then the warm-up steps
     for t in range(warmup + steps):
         s = rng.random(mask.shape, dtype=np.float32)
         s[~mask] = -1.0
@@ -205,7 +211,7 @@ def run_reference_arm(args, rank: int, world: int):
     # calibrate a bounded sample so warmup+steps finish in ~2 minutes
     rate, _, _ = cpu_env_steps_per_s(4096, 3, 1, threads)
     budget_s = 100.0
-    n = int(max(1024, min(ENVS_PER_GPU, rate * budget_s / max(1, args.steps + args.warmup))))
+    n = int(max(1024, min(ENVS_PER_GPU, rate * budget_s / max(1, args.steps + args.warmup + PRE_ROLL))))
     n = 1 << (n.bit_length() - 1)
     value, total, per_step = cpu_env_steps_per_s(n, args.steps, args.warmup, threads)
     sample = f"{n} envs x {args.steps} steps, {H}x{W}x{MINES} random valid actions, oracle/msw_oracle.c (C port), {threads} threads"
@@ -242,15 +248,18 @@ def time_env_steps(torch, m, dev, rank, world, barrier, board, n_envs, K, Wm, ri
     log = torch.empty((Wm + keep_actions + 1, n_envs), dtype=torch.int32, device=dev) if keep_actions else None
     scratch = torch.empty((n_envs,), dtype=torch.int32, device=dev)
     vec.reset(out=slots[0])
-    for t in range(Wm):
-        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=log[t] if keep_actions else scratch)
+    for t in range(PRE_ROLL):                                    # workload setup: stationary mix of episode phases
+        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
+    Wm0, Wm = Wm, Wm + PRE_ROLL                                  # step indices continue after the pre-roll
+    for t in range(PRE_ROLL, Wm):
+        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=log[t - PRE_ROLL] if keep_actions else scratch)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(torch, dev.index)
     barrier()
     sampler.start()
     ev0.record()
     for t in range(K):
-        a = log[Wm + min(t, keep_actions)] if keep_actions else scratch
+        a = log[Wm0 + min(t, keep_actions)] if keep_actions else scratch
         vec.step_random(Wm + t, valid_only=valid_only, out=slots[t % ring], actions_out=a)   # policy + step: one launch
     ev1.record()
     clocks = sampler.finish()          # sampled while the last launches are still executing
@@ -319,6 +328,14 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         v = make_env()
         v.host_delta = delta
         v.reset()
+        scratch = torch.empty((N,), dtype=torch.int32, device=dev)
+        pre = m.StepOut(obs=torch.empty((N, 10, H, W), dtype=torch.float32, device=dev),
+                        action_mask=torch.empty((N, H * W), dtype=torch.bool, device=dev),
+                        rewards=torch.empty((N,), dtype=torch.float32, device=dev),
+                        dones=torch.empty((N,), dtype=torch.bool, device=dev))
+        for t in range(PRE_ROLL):              # the same untimed pre-roll as the device-timed leg (same trajectory)
+            v.step_random(t, valid_only=VALID_ONLY, out=pre, actions_out=scratch)
+        del pre, scratch
         for t in range(Wm):
             v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
         rows = [acts_host[Wm + t] for t in range(steps)]

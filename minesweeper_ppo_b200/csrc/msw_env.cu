@@ -1026,7 +1026,7 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     }
     // Reference-shaped observation / mask on the host: NOT copied (41*HW bytes per env would make the call
     // PCIe-bound); the packed post-step state they are a pure function of (2*wpb + 4 words per env) is copied
-    // into the caller's pinned staging area and expanded on the host after the sync (msw_host_expand.cu).
+    // into the caller's pinned staging area and expanded on the host after the sync (msw_host_expand.cpp).
     const bool expand = h && (h->obs || h->mask);
     const size_t wpb = (size_t)p.wpb;
     if (expand) {

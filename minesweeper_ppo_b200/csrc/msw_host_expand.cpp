@@ -25,6 +25,7 @@
 #include "msw_error.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <immintrin.h>
 #include <functional>
@@ -39,7 +40,10 @@ namespace msw {
 
 namespace {
 
-// ---- a small persistent worker pool (the library owns no device memory; host threads are fine)
+// ---- a small persistent worker pool (the library owns no device memory; host threads are fine).
+// One parallel region per msw_step_host call, ~1 ms of work: waking sleeping threads through a condition variable
+// costs ~100 us of that, so an idle worker first SPINS on the region counter for SPIN_US (the next step's region
+// normally arrives within that time when steps are issued back to back) and only then sleeps.
 class HostPool {
 public:
     static HostPool &get()
@@ -51,29 +55,39 @@ public:
     void run(int threads, long long chunks, const std::function<void(long long)> &fn)
     {
         if (threads < 1) threads = 1;
+        if (threads > 4096) threads = 4096;
         if (chunks <= 1 || threads == 1) {
             for (long long c = 0; c < chunks; ++c) fn(c);
             return;
         }
         std::unique_lock<std::mutex> call_lock(call_mu_);     // one parallel region at a time
         grow(threads - 1);
+        fn_ = &fn;
+        chunks_ = chunks;
+        next_.store(0, std::memory_order_relaxed);
+        pending_.store(threads - 1, std::memory_order_relaxed);
+        const unsigned long long gen = (state_.load(std::memory_order_relaxed) >> 16) + 1;
         {
-            std::lock_guard<std::mutex> g(mu_);
-            fn_ = &fn;
-            chunks_ = chunks;
-            next_.store(0, std::memory_order_relaxed);
-            active_ = threads - 1;
-            pending_ = active_;
-            ++generation_;
+            std::lock_guard<std::mutex> g(mu_);                // pairs with the sleepers' predicate check
+            state_.store(gen << 16 | (unsigned long long)(threads - 1), std::memory_order_release);
         }
-        cv_work_.notify_all();
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_work_.notify_all();
         work();
-        std::unique_lock<std::mutex> g(mu_);
-        cv_done_.wait(g, [&] { return pending_ == 0; });
+        for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins) {
+            if (spins < 20000) cpu_relax();
+            else sched_yield();
+        }
         fn_ = nullptr;
     }
 
 private:
+    static constexpr long long SPIN_US = 400;
+    static void cpu_relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        _mm_pause();
+#endif
+    }
     void work()
     {
         for (;;) {
@@ -92,29 +106,40 @@ private:
     }
     void loop(int id)
     {
-        unsigned long long seen = 0;
+        unsigned long long seen = 0;                          // region counter this worker has handled
         for (;;) {
-            {
-                std::unique_lock<std::mutex> g(mu_);
-                cv_work_.wait(g, [&] { return generation_ != seen; });
-                seen = generation_;
-                if (id >= active_) continue;                  // this region uses fewer threads
+            unsigned long long st = state_.load(std::memory_order_acquire);
+            if ((st >> 16) == seen) {
+                const auto t0 = std::chrono::steady_clock::now();
+                for (unsigned spins = 1;; ++spins) {
+                    cpu_relax();
+                    st = state_.load(std::memory_order_acquire);
+                    if ((st >> 16) != seen) break;
+                    if ((spins & 127u) == 0 &&
+                        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > SPIN_US) {
+                        std::unique_lock<std::mutex> g(mu_);
+                        sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                        cv_work_.wait(g, [&] { return (state_.load(std::memory_order_acquire) >> 16) != seen; });
+                        sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+                        st = state_.load(std::memory_order_acquire);
+                        break;
+                    }
+                }
             }
+            seen = st >> 16;
+            if (id >= (int)(st & 0xffffu)) continue;          // this region uses fewer threads
             work();
-            {
-                std::lock_guard<std::mutex> g(mu_);
-                if (--pending_ == 0) cv_done_.notify_one();
-            }
+            pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
     std::mutex call_mu_, mu_;
-    std::condition_variable cv_work_, cv_done_;
+    std::condition_variable cv_work_;
     std::vector<std::thread> workers_;
     const std::function<void(long long)> *fn_ = nullptr;
     std::atomic<long long> next_{0};
+    std::atomic<unsigned long long> state_{0};                // region counter << 16 | workers taking part
+    std::atomic<int> pending_{0}, sleepers_{0};
     long long chunks_ = 0;
-    int active_ = 0, pending_ = 0;
-    unsigned long long generation_ = 0;
 };
 
 struct Luts {

@@ -26,6 +26,7 @@ device the constructor raises.
 from __future__ import annotations
 
 import ctypes as C
+from collections.abc import Sequence
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple, Union
 
@@ -134,6 +135,41 @@ class _EnvList:
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
+
+
+class _LazyList(Sequence):
+    """A read-only list whose items are made on access (the per-env `infos` lists of VecMinesweeper.step,
+    env.py:485-505).  Compares equal to the list / tuple / sequence with the same items."""
+    __slots__ = ("_n", "_item")
+
+    def __init__(self, n: int, item):
+        self._n, self._item = int(n), item
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._item(k) for k in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError("list index out of range")
+        return self._item(i)
+
+    def __iter__(self):
+        return (self._item(k) for k in range(self._n))
+
+    def __eq__(self, other):
+        if not isinstance(other, (list, tuple, Sequence)) or isinstance(other, (str, bytes)):
+            return NotImplemented
+        return len(other) == self._n and all(a == b for a, b in zip(self, other))
+
+    __hash__ = None
+
+    def __repr__(self) -> str:
+        return repr(list(self))
 
 
 class _ResultSet:
@@ -658,12 +694,16 @@ class VecMinesweeper:
             step, rc = pin["step"].numpy(), pin["revealed_count"].numpy()
             batch = {"obs": res["obs"], "action_mask": res["mask"]}
             del res
+        # env.py:485-505: per-env Python lists.  Building N dicts costs more than the whole step at large N and
+        # train_rl.py:242 never looks at them, so the lists are lazy sequences over copies of the scalar arrays:
+        # same indexing / len / iteration / equality as the reference's lists, items made on access.
         hw = max(1, self.HW)
-        infos = {                                                     # env.py:485-505
-            "aux": [{"step": s_, "last_new_reveals": r_, "revealed_frac": c_ / hw}
-                    for s_, r_, c_ in zip(step.tolist(), newr.tolist(), rc.tolist())],
-            "outcome": [_OUTCOME_NAMES[o] for o in outcome.tolist()],
-            "done": dones.tolist(),
+        step, newr, rc, outcome, done_i = step.copy(), newr.copy(), rc.copy(), outcome.copy(), dones.copy()
+        infos = {
+            "aux": _LazyList(n, lambda i: {"step": int(step[i]), "last_new_reveals": int(newr[i]),
+                                           "revealed_frac": int(rc[i]) / hw}),
+            "outcome": _LazyList(n, lambda i: _OUTCOME_NAMES[outcome[i]]),
+            "done": _LazyList(n, lambda i: bool(done_i[i])),
         }
         return batch, rewards, dones, infos
 

@@ -64,6 +64,6 @@ for sets in (0, 1, 2):
         times.append(time.perf_counter() - t0)
     steady = times[max(1, sets) + 1:]
     name = "full expansion" if sets == 0 else f"delta, {sets} result array set(s)"
-    print(f"{name:32s}: first call {times[0] * 1e3:7.2f} ms, steady {np.median(steady) * 1e3:7.2f} ms  "
+    print(f"{name:32s}: first call {times[0] * 1e3:7.2f} ms, steady {np.median(steady) * 1e3:7.2f} ms (min {min(steady) * 1e3:.2f})  "
           f"{N / np.median(steady) / 1e6:7.2f} M env/s   (threads={TH or os.cpu_count()})")
     del pool
