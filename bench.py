@@ -324,6 +324,8 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     del actions_log
     torch.cuda.empty_cache()
 
+    step_ms = {}
+
     def run_host(copy_obs: bool, steps: int, delta: bool = True):
         v = make_env()
         v.host_delta = delta
@@ -336,20 +338,24 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         for t in range(PRE_ROLL):              # the same untimed pre-roll as the device-timed leg (same trajectory)
             v.step_random(t, valid_only=VALID_ONLY, out=pre, actions_out=scratch)
         del pre, scratch
-        for t in range(Wm):
-            v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
+        pin = None
+        for t in range(Wm):                    # warm up exactly as the timed loop runs: the previous result stays referenced
+            pin = v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
         rows = [acts_host[Wm + t] for t in range(steps)]
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         done_count = 0
+        stamps = [t0]
         for a in rows:
             pin = v.step_host(a, copy_obs=copy_obs, copy_infos=False)
             done_count += int(np.count_nonzero(pin["done"].numpy()))   # the host really reads the result
+            stamps.append(time.perf_counter())
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        step_ms[(copy_obs, delta)] = [round(1e3 * (b - a), 4) for a, b in zip(stamps[:-1], stamps[1:])][:64]
         return max(e0.elapsed_time(e1) / 1e3, wall), wall, done_count
 
     if args.no_e2e:
@@ -407,6 +413,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
             "call": "msw_step_host via VecMinesweeper.step_host(copy_obs=False): pinned int32 actions in, "
                     "pinned reward f32 + done bool out, stream-synchronised every step; obs/mask stay in HBM "
                     "for the policy (the reference copies obs host->device at this point, train_rl.py:198-199)",
+            "step_ms": step_ms.get((False, True)),
         },
         "e2e_host_obs": {
             "value": total_envs * Kh / e2e_full_max, "unit": UNIT, "steps": Kh,
@@ -421,6 +428,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
                              "note": f"host_delta=False: every byte of obs/mask rewritten each step "
                                      f"({(41 * H * W) * N / 1e6:.0f} MB, bound by host store bandwidth)"},
             "host_threads": host_threads(),
+            "step_ms": step_ms.get((True, True)),
         },
         "gpu_launches": K,
         "gae": gae_info,
