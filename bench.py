@@ -325,6 +325,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     torch.cuda.empty_cache()
 
     step_ms = {}
+    exp_threads = max(1, host_threads() // world)      # host threads of the NumPy-result expansion: the box's cores / ranks
 
     def run_host(copy_obs: bool, steps: int, delta: bool = True):
         v = make_env()
@@ -340,7 +341,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         del pre, scratch
         pin = None
         for t in range(Wm):                    # warm up exactly as the timed loop runs: the previous result stays referenced
-            pin = v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False)
+            pin = v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False, threads=exp_threads)
         rows = [acts_host[Wm + t] for t in range(steps)]
         barrier()
         t0 = time.perf_counter()
@@ -349,7 +350,7 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         done_count = 0
         stamps = [t0]
         for a in rows:
-            pin = v.step_host(a, copy_obs=copy_obs, copy_infos=False)
+            pin = v.step_host(a, copy_obs=copy_obs, copy_infos=False, threads=exp_threads)
             done_count += int(np.count_nonzero(pin["done"].numpy()))   # the host really reads the result
             stamps.append(time.perf_counter())
         e1.record()
@@ -420,14 +421,14 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
             "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": host_obs_d2h_bytes(m, N),
             "call": "same call with copy_obs=True: the full reference-shaped NumPy result (obs fp32 [N,10,H,W] + mask + "
                     "reward + done) in host memory every step.  The planes do not cross PCIe: msw_step_host copies the "
-                    "packed post-step state (85 B/env) and expands it on all host threads (msw_host_expand.cpp).  The "
+                    "packed mine + revealed bitboards (64 B/env, in slices that overlap the expansion) and expands them on the host threads (msw_host_expand.cpp).  The "
                     "result arrays are recycled (two sets alternate here, as in any loop that keeps the previous batch) "
                     "and each carries a shadow of the bit planes it holds, so only the cache lines that changed since "
                     "the set was last filled are rewritten (non-temporal stores)",
             "full_rewrite": {"value": total_envs * Kf / e2e_rewrite_max, "steps": Kf,
                              "note": f"host_delta=False: every byte of obs/mask rewritten each step "
                                      f"({(41 * H * W) * N / 1e6:.0f} MB, bound by host store bandwidth)"},
-            "host_threads": host_threads(),
+            "host_threads_per_rank": exp_threads,
             "step_ms": step_ms.get((True, True)),
         },
         "gpu_launches": K,

@@ -338,7 +338,8 @@ typedef struct msw_host_out {
 } msw_host_out;
 
 /* The host-side expansion on its own: packed state arrays IN HOST MEMORY (h_mines / h_revealed int32 [n][wpb],
- * h_meta int32 [n][4], layouts of msw_state) -> _build_obs (env.py:172-192) / _compute_action_mask
+ * h_meta int32 [n][4], layouts of msw_state; h_meta may be NULL: first_click_done only gates the count planes of
+ * REVEALED cells, and a cell can only be revealed after the first click) -> _build_obs (env.py:172-192) / _compute_action_mask
  * (env.py:194-196) arrays in host memory.  Pure host function (no CUDA call), used by msw_step_host and by
  * VecMinesweeper.reset() in the NumPy convention. */
 int msw_expand_obs_host(const msw_env_desc *desc, const int32_t *h_mines, const int32_t *h_revealed,

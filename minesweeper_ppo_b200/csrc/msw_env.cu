@@ -1024,18 +1024,12 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
         if (!(dev)) return fail(MSW_ERR_NULL, "host output " #field " requested without device staging"); \
         d2h(h->field, dev, bytes);                                                                         \
     }
-    // Reference-shaped observation / mask on the host: NOT copied (41*HW bytes per env would make the call
-    // PCIe-bound); the packed post-step state they are a pure function of (2*wpb + 4 words per env) is copied
-    // into the caller's pinned staging area and expanded on the host after the sync (msw_host_expand.cpp).
     const bool expand = h && (h->obs || h->mask);
     const size_t wpb = (size_t)p.wpb;
     if (expand) {
         if (!h->stage) return fail(MSW_ERR_NULL, "msw_step_host: host obs/mask requested without the pinned state staging area");
         if (h->shadow && !(h->obs && h->mask))
             return fail(MSW_ERR_NULL, "msw_step_host: a shadow describes BOTH result arrays: obs and mask are required with it");
-        d2h(h->stage, st->mines, N * wpb * 4);
-        d2h(h->stage + N * wpb, st->revealed, N * wpb * 4);
-        d2h(h->stage + 2 * N * wpb, st->meta, N * 16);
     }
     MSW_HOST_SCALAR(reward, p.reward, float, N * 4)
     MSW_HOST_SCALAR(done, p.done, uint8_t, N)
@@ -1051,10 +1045,49 @@ extern "C" int msw_step_host(const msw_env_desc *desc, const msw_state *st, cons
     if ((rc = launch_env<MODE_STEP>(p, s))) return rc;
     for (int i = 0; i < nc; ++i)
         MSW_CUDA_TRY(cudaMemcpyAsync(copies[i].dst, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToHost, s));
+    if (!expand) {
+        MSW_CUDA_TRY(cudaStreamSynchronize(s));
+        return MSW_OK;
+    }
+    // Reference-shaped observation / mask on the host: NOT copied (41*HW bytes per env would make the call
+    // PCIe-bound); the packed post-step state they are a pure function of -- the mine and revealed bitboards,
+    // 2*wpb words per env; first_click_done is implied (a cell can only be revealed after the first click,
+    // env.py:119-122, so revealed != 0 <=> first_click_done wherever it matters) -- is copied into the caller's
+    // pinned staging area and expanded on the host (msw_host_expand.cpp).  The copy travels in up to four slices
+    // with an event after each, so the host expands slice k while slices k+1.. are still on the bus.
+    uint32_t *h_mines = reinterpret_cast<uint32_t *>(h->stage), *h_rev = h_mines + N * wpb;
+    constexpr int MAX_SLICES = 4;
+    const int slices = N >= 32768 ? MAX_SLICES : 1;
+    const size_t per = ((N + slices - 1) / slices + 127) / 128 * 128;
+    cudaEvent_t ev[MAX_SLICES] = {};
+    int made = 0;
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < slices && err == cudaSuccess; ++k) {
+        const size_t lo = (size_t)k * per, hi = lo + per < N ? lo + per : N;
+        if (lo >= hi) break;
+        err = cudaMemcpyAsync(h_mines + lo * wpb, st->mines + lo * wpb, (hi - lo) * wpb * 4, cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(h_rev + lo * wpb, st->revealed + lo * wpb, (hi - lo) * wpb * 4, cudaMemcpyDeviceToHost, s);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        if (err == cudaSuccess) {
+            ++made;
+            err = cudaEventRecord(ev[k], s);
+        }
+    }
+    for (int k = 0; k < made && err == cudaSuccess; ++k) {
+        const size_t lo = (size_t)k * per, hi = lo + per < N ? lo + per : N;
+        err = cudaEventSynchronize(ev[k]);
+        if (err == cudaSuccess)
+            expand_obs_host(p.H, p.W, h_mines + lo * wpb, h_rev + lo * wpb, nullptr, (long long)(hi - lo),
+                            h->obs ? h->obs + lo * MSW_OBS_CHANNELS * HW : nullptr, h->mask ? h->mask + lo * HW : nullptr,
+                            h->shadow ? h->shadow + lo * (size_t)msw_shadow_words(p.H, p.W) : nullptr, h->shadow_valid, h->threads);
+    }
+    for (int k = 0; k < made; ++k) cudaEventDestroy(ev[k]);
+    if (err != cudaSuccess) {
+        cudaStreamSynchronize(s);                    // nothing of this call may still be in flight when it returns
+        return cuda_fail(err, "msw_step_host: state copy / expansion");
+    }
     MSW_CUDA_TRY(cudaStreamSynchronize(s));
-    if (expand)
-        expand_obs_host(p.H, p.W, reinterpret_cast<const uint32_t *>(h->stage), reinterpret_cast<const uint32_t *>(h->stage + N * wpb),
-                        h->stage + 2 * N * wpb, (long long)n, h->obs, h->mask, h->shadow, h->shadow_valid, h->threads);
     return MSW_OK;
 }
 

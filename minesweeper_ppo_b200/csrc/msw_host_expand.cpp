@@ -5,8 +5,8 @@
 //
 // Why: the step itself runs on the GPU either way, but the reference-shaped result is 41*HW bytes per env
 // (10.5 KB at 16x16) and crossing PCIe with it caps msw_step_host at ~5e6 env-steps/s (the speed of a 16-thread
-// CPU port).  The state the observation is a pure function of -- mines, revealed, first_click_done -- is
-// 2*ceil(HW/32)*4 + 16 bytes per env (80 B at 16x16), so msw_step_host copies THAT device->host and expands it
+// CPU port).  The state the observation is a pure function of -- the mine and revealed bitboards -- is
+// 2*ceil(HW/32)*4 bytes per env (64 B at 16x16), so msw_step_host copies THAT device->host and expands it
 // here, straight into the caller's (ordinary, unpinned) result arrays with non-temporal stores.  This is a
 // format conversion of the GPU's result, not a CPU implementation of the env: no game logic runs here.
 //
@@ -275,7 +275,7 @@ void expand_range(const uint32_t *mines, const uint32_t *revealed, const int32_t
     const int HW = H * W, wpb = (HW + 31) / 32, SW = shadow_words_for(HW);
     uint64_t planes[PLANE_WORDS_MAX];
     for (long long i = lo; i < hi; ++i) {
-        build_planes(mines + i * wpb, revealed + i * wpb, meta[4 * i], H, W, wpb, planes, SW);
+        build_planes(mines + i * wpb, revealed + i * wpb, meta ? meta[4 * i] : 1, H, W, wpb, planes, SW);
         uint64_t *sh = shadow ? shadow + i * SW : nullptr;
         emit_env<STREAM>(planes, (sh && valid) ? sh : nullptr, HW, obs ? obs + (size_t)i * MSW_OBS_CHANNELS * HW : nullptr,
                          mask ? mask + (size_t)i * HW : nullptr, L);
@@ -303,7 +303,7 @@ __attribute__((target("avx2"))) void expand16_range(const uint32_t *mines, const
         const __m256i R = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(revealed + i * 8));
         __m256i pl[MSW_OBS_CHANNELS];
         pl[0] = R;
-        if (meta[4 * i] && !_mm256_testz_si256(R, R)) {                                       // env.py:181
+        if ((!meta || meta[4 * i]) && !_mm256_testz_si256(R, R)) {                                       // env.py:181
             const __m256i M = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(mines + i * 8));
             const __m256i up = _mm256_alignr_epi8(M, _mm256_permute2x128_si256(M, M, 0x08), 14);   // lane r = row r-1
             const __m256i dn = _mm256_alignr_epi8(_mm256_permute2x128_si256(M, M, 0x81), M, 2);    // lane r = row r+1
@@ -381,7 +381,8 @@ int host_thread_count(int requested)
     return hc ? (int)hc : 1;
 }
 
-// mines / revealed: [n][wpb] words, meta: [n][4] (word 0 = first_click_done); obs [n][10][H][W] / mask [n][HW] nullable.
+// mines / revealed: [n][wpb] words, meta: [n][4] (word 0 = first_click_done; nullable: a cell can only be revealed
+// after the first click, so first_click_done is implied wherever it matters); obs [n][10][H][W] / mask [n][HW] nullable.
 // shadow (nullable): [n][msw_shadow_words(H, W)] -- the bit planes obs / mask hold; shadow_valid = 0: the arrays
 // hold anything (everything is written and the shadow initialised), != 0: only what differs is rewritten.
 void expand_obs_host(int H, int W, const uint32_t *mines, const uint32_t *revealed, const int32_t *meta, long long n,
@@ -422,7 +423,8 @@ void expand_obs_host(int H, int W, const uint32_t *mines, const uint32_t *reveal
 static int check_expand_args(const msw_env_desc *desc, const void *a, const void *b, const void *c, int64_t n, const char *who)
 {
     using namespace msw;
-    if (!desc || !a || !b || !c) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
+    (void)c;                                           // h_meta may be NULL
+    if (!desc || !a || !b) return fail(MSW_ERR_NULL, "%s: NULL pointer", who);
     if (msw_words_per_board(desc->H, desc->W) == 0)
         return fail(MSW_ERR_BAD_SHAPE, "%s: unsupported board %dx%d", who, desc->H, desc->W);
     if (n < 0) return fail(MSW_ERR_BAD_SHAPE, "%s: n=%lld", who, (long long)n);

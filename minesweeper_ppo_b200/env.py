@@ -26,6 +26,7 @@ device the constructor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections.abc import Sequence
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple, Union
@@ -247,6 +248,13 @@ class VecMinesweeper:
         self._pinned_ok: set = set()
         self._result_pool: list = []
         self.host_delta = True       # NumPy convention: rewrite only what changed in a recycled result set (step_host)
+        # host threads of the NumPy-result expansion: the CPUs this process may use, shared between the ranks
+        # torchrun started on this node (one process per GPU)
+        try:
+            cpus = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cpus = os.cpu_count() or 1
+        self.host_threads = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))
         self._staging: Dict[str, torch.Tensor] = {}
         # late-start curriculum (env.py:397-403, 416-466): parameters normalised as the reference does
         self._late = None
@@ -555,7 +563,7 @@ class VecMinesweeper:
         """Device->host bytes per step of the reference calling convention: packed state + reward + done
         (the fp32 planes are expanded on the host, they do not cross PCIe)."""
         wpb = (H * W + 31) // 32
-        return n * ((2 * wpb + 4) * 4 + 5)
+        return n * (2 * wpb * 4 + 5)
 
     def _result_arrays(self) -> "_ResultSet":
         """(obs f32 [n,10,H,W], mask bool [n,HW]) for the next result.  The reference returns fresh arrays every
@@ -646,7 +654,7 @@ class VecMinesweeper:
             rset.valid = 0                                     # until the call has succeeded
         else:
             h.shadow, h.shadow_valid = None, 0
-        h.threads = int(threads)
+        h.threads = int(threads) if threads else self.host_threads
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
         if torch.cuda.current_device() == self.device.index:

@@ -105,7 +105,8 @@ def test_delta_expansion_tracks_a_trajectory(oracle, H, W, M, sets, threads, ali
         meta = np.zeros((N, 4), np.int32)
         meta[:, 0] = vec.first_click_done
         e = pool[t % sets]
-        rc = L.msw_expand_obs_host_delta(C.byref(desc), mines.ctypes.data, rev.ctypes.data, meta.ctypes.data, N,
+        # h_meta may be NULL (odd steps): first_click_done is implied by revealed != 0, which is how msw_step_host calls it
+        rc = L.msw_expand_obs_host_delta(C.byref(desc), mines.ctypes.data, rev.ctypes.data, meta.ctypes.data if t % 2 == 0 else None, N,
                                          e[0].ctypes.data, e[1].ctypes.data, e[2].ctypes.data, e[3], threads)
         assert rc == 0
         e[3] = 1
