@@ -38,6 +38,7 @@ from . import _lib
 
 OBS_CHANNELS = _lib.OBS_CHANNELS
 _OUTCOME_NAMES = (None, "win", "loss")
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 @dataclass
@@ -279,6 +280,10 @@ class VecMinesweeper:
         s.flags = self._flags.data_ptr() if self._flags is not None else None
 
     def _stream(self) -> int:
+        """cudaStream_t of torch's current stream on the env's device (the raw getter skips building a Stream object:
+        ~2 us per call, which is 1.5 % of a host-buffer step)."""
+        if _raw_stream is not None:
+            return _raw_stream(self.device.index)
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _check(self, t: Optional[torch.Tensor], shape, dtype, name: str) -> Optional[int]:

@@ -32,6 +32,12 @@ def wall(fn, n=K):
 
 us_full = wall(lambda i: v.step_host(acts[i], copy_obs=False, copy_infos=False))
 us_full_read = wall(lambda i: int(np.count_nonzero(v.step_host(acts[i], copy_obs=False, copy_infos=False)["done"].numpy())))
+# the C-ABI call alone (prepared argument structs, no Python mirror work around it)
+_key = (False, False, v.aux_maps)
+_io, _h, _rd, _rs, _rio, _rh = v._host_calls[_key]
+_stream = torch.cuda.current_stream().cuda_stream
+_ptrs = [acts[i].data_ptr() for i in range(K + 8)]
+us_c = wall(lambda i: v._L.msw_step_host(_rd, _rs, _rio, _ptrs[i], _rh, N, _stream))
 d_act = torch.empty((N,), dtype=torch.int32, device=dev)
 out = v._alloc_encode()
 out.rewards = torch.empty((N,), device=dev); out.dones = torch.empty((N,), dtype=torch.bool, device=dev)
@@ -70,7 +76,32 @@ def sync_only(i):
     torch.cuda.current_stream().synchronize()
 
 
+# the same three operations captured once in a CUDA graph (fixed pinned source / destination) and replayed: what a
+# graph-replaying msw_step_host could reach for a caller that reuses ONE pinned action buffer (built, measured at
+# 135 us against 141 us, no gain for rotating buffers, removed: profiles/experiments/r02w_step_host_graph_replay.patch)
+stage_in = torch.empty((N,), dtype=torch.int32).pin_memory()
+gout = v._alloc_encode()
+gout.rewards = dev_out[:N * 4].view(torch.float32); gout.dones = dev_out[N * 4:].view(torch.bool)
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    for _ in range(3):
+        d_act.copy_(stage_in, non_blocking=True); v.step(d_act, out=gout, want_infos=False); pin_out.copy_(dev_out, non_blocking=True)
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        d_act.copy_(stage_in, non_blocking=True); v.step(d_act, out=gout, want_infos=False); pin_out.copy_(dev_out, non_blocking=True)
+
+
+def graph_step(i):
+    g.replay()
+    side.synchronize()
+
+
+stage_in.copy_(acts[0])
+us_graph = wall(graph_step)
 print(f"msw_step_host (actions in, reward+done out, sync)      : {us_full:7.1f} us / call  -> {N / us_full:.1f} M env-steps/s")
+print(f"  the C-ABI call alone (ctypes, prepared structs)        : {us_c:7.1f} us / call")
+print(f"  H2D + step + D2H captured in one CUDA graph, replay + sync: {us_graph:7.1f} us / call (fixed action: mostly no-op clicks)")
 print(f"  + the host reads the done flags (np.count_nonzero)    : {us_full_read:7.1f} us / call")
 print(f"step launch on device actions + stream sync             : {us_kernel:7.1f} us   (device time of the kernel back to back: {us_kernel_dev:.1f} us)")
 print(f"H2D 256 KB + stream sync                                : {wall(h2d_only):7.1f} us")
