@@ -567,7 +567,7 @@ def bench_gae(torch, m, dev):
             "note": "cold = inputs in HBM, CUDA events around one launch (about 3 us of that is event/launch gap: ncu "
                     "shows 11 us); back_to_back = 20 launches replayed from one CUDA graph (17.9 MB working set stays "
                     "in L2, as it does right after a rollout); at C3 size the kernel is latency-bound (8,192 chains "
-                    "of 128 dependent steps, one 36 KB tile per CTA); `large` is the same kernel at 64x the columns, "
+                    "of 128 dependent steps, four 9 KB slices per CTA through the ring); `large` is the same kernel at 64x the columns, "
                     "where it is HBM-bound"}
 
 

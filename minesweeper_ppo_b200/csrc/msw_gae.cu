@@ -10,16 +10,15 @@
 //     last  = delta + ((gamma*lam) * nnt) * last                      (:91)
 //     returns = advantages + values                                   (:94)
 // Storage is time-major [T][N] (buffers.py:81-83), so a row of 32 consecutive
-// columns is one 128-byte line.  A CTA owns 16 or 32 columns: all 8 warps stream
-// the [TC x COLS] tiles of rewards / values / dones into shared memory with
-// coalesced loads (the only way to get enough bytes in flight when N is a few
-// thousand columns).  Only `last` carries a dependency from t+1 to t -- next_value is
-// values[t+1], plain data -- so all 256 threads then form delta[t] for their own
-// elements in place, and the one warp that walks the chains does just
-// FSEL / FMUL / FADD per step out of shared memory.  All warps write advantages /
-// returns back coalesced.  HBM-bound in principle (17 B per transition) but
-// latency-bound at the reference's sizes: forming delta inside the serial walk instead
-// takes the same 14.3 us (A/B in one process, round 1), i.e. the walk is not the long pole.
+// columns is one 128-byte line and a CTA owns 32 columns.  Only `last` carries a
+// dependency from t+1 to t -- next_value is values[t+1], plain data -- so delta[t]
+// is formed for all elements in parallel and the one warp that walks the chains
+// does just FSEL / FMUL / FADD per step out of shared memory / registers.
+// Two kernels share that arithmetic: gae_pipe_kernel (TMA slices through a
+// shared-memory ring, warp-specialised; the default) and gae_kernel (plain
+// coalesced loads, for ragged N the tensor maps cannot describe).  HBM-bound when
+// there are many columns (17 B per transition), latency-bound at the reference's
+// sizes, where the serial walk is the critical path.
 #include "../../include/msw_b200.h"
 #include "msw_error.h"
 
@@ -140,30 +139,8 @@ gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
 }
 
 // ---------------------------------------------------------------------------
-// TMA variant (the default when N % 16 == 0 and the arrays are 16-byte aligned).  Measured on one B200
-// (profiles/r01g_gae.md): the same 7.1 us as the plain-load kernel at C3 size (T=128, N=8,192: both are
-// latency-bound, one tile per CTA), but 5.1 TB/s instead of 2.6 TB/s at N=524,288, where the kernel is
-// HBM-bound.
-//
-// The tile loads and stores above cost 48 LDG + 48 STS + 32 STG per thread plus their address
-// arithmetic, and the memory system sees them as ~100 k separate 128-byte requests.  Here one
-// thread moves each [128 x 32] tile with a single cp.async.bulk.tensor.2d (rewards, values, dones
-// in; advantages, returns out), completion on an mbarrier, so the CTA's whole 36 KB is in flight
-// from the first cycle and no thread spends instructions on the copies.  Out-of-range rows and
-// columns are zero-filled on load and clipped on store by the tensor map, so ragged T and N need
-// no predicates.  Arithmetic and its order are exactly those of gae_kernel above.
+// TMA helpers (cp.async.bulk.tensor.2d loads completing on an mbarrier, bulk-group stores, elect.sync)
 // ---------------------------------------------------------------------------
-constexpr int TG_ROWS = 128, TG_COLS = 32, TG_THREADS = 128;
-
-struct TmaGaeSmem {
-    alignas(128) float r[TG_ROWS][TG_COLS];      // rewards in, delta, advantages out
-    alignas(128) float v[TG_ROWS][TG_COLS];      // values in, returns out
-    alignas(128) float c[TG_ROWS][TG_COLS];      // (gamma*lam) * nnt
-    alignas(128) uint8_t d[TG_ROWS][TG_COLS];
-    float gvn[TG_COLS];                          // gamma * value of the row after this tile's last one
-    alignas(8) unsigned long long bar;
-};
-
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
@@ -184,93 +161,182 @@ __device__ __forceinline__ bool elect_one()      // one lane of a converged warp
     return pred != 0u;
 }
 
-__global__ void __launch_bounds__(TG_THREADS)
-gae_tma_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_constant__ CUtensorMap m_values,
-               const __grid_constant__ CUtensorMap m_dones, const __grid_constant__ CUtensorMap m_adv,
-               const __grid_constant__ CUtensorMap m_ret, const float *__restrict__ last_values, long long T,
-               long long N, float gamma, float gamma_lam, int prescaled)
+// ---------------------------------------------------------------------------
+// TMA kernel (the default when N % 16 == 0 and the arrays are 16-byte aligned): the same arithmetic in [32 x 32]
+// time slices through a 4-stage shared-memory ring, with the three kinds of work on different warps so that only
+// the serial walk is on a CTA's critical path:
+//   warp 4   (producer) keeps up to four slices in flight (one cp.async.bulk.tensor.2d per array and slice ->
+//            `full` mbarriers; out-of-range rows / columns are zero-filled on load and clipped on store by the
+//            tensor map, so ragged T and N need no predicates), streams finished slices out with TMA stores and
+//            refills a stage as soon as its stores have read it;
+//   warps 1-3 (delta)   form delta[t] for a slice as soon as it lands -- gamma*v[t+1] across a slice boundary comes
+//            from a register they saved while the previous slice's values were still untouched -> `dd` mbarriers;
+//   warp 0   (walk)     runs last = delta + c*last down the slice and forms returns = advantages + values in the
+//            same pass (off the dependent chain) -> `done` mbarriers.
+// Slices are processed newest-time-first; every operation and its order are those of gae_kernel above.
+// Measured on one B200 (profiles/r02x_gae_ab.txt) against round 2's first TMA kernel, which moved whole [128 x 32]
+// tiles load -> delta -> walk -> store with nothing overlapping inside a CTA (commit 9cc9c01): T=128, N=8,192
+// 5.2 vs 7.0 us back to back, 12.3 vs 14.3 us cold; N=524,288 (HBM-bound) 186 vs 222 us = 6.13 vs 5.15 TB/s
+// (0.94 vs 0.79 of the measured copy peak).
+// ---------------------------------------------------------------------------
+constexpr int PG_ROWS = 32, PG_COLS = 32, PG_STAGES = 4, PG_DWARPS = 3, PG_THREADS = (1 + PG_DWARPS + 1) * 32;
+
+struct PipeStage {
+    alignas(128) float r[PG_ROWS][PG_COLS];      // rewards in, delta, advantages out
+    alignas(128) float v[PG_ROWS][PG_COLS];      // values in, returns out
+    alignas(128) uint8_t d[PG_ROWS][PG_COLS];
+};
+struct PipeSmem {
+    PipeStage st[PG_STAGES];
+    alignas(8) unsigned long long full[PG_STAGES], dd[PG_STAGES], done[PG_STAGES];
+};
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+template <int BATCH>
+__global__ void __launch_bounds__(PG_THREADS, BATCH == PG_ROWS ? 1 : 5)
+gae_pipe_kernel(const __grid_constant__ CUtensorMap m_rewards, const __grid_constant__ CUtensorMap m_values,
+                const __grid_constant__ CUtensorMap m_dones, const __grid_constant__ CUtensorMap m_adv,
+                const __grid_constant__ CUtensorMap m_ret, const float *__restrict__ last_values, long long T,
+                long long N, float gamma, float gamma_lam, int prescaled)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TmaGaeSmem &S = *reinterpret_cast<TmaGaeSmem *>(smem_raw);
+    PipeSmem &S = *reinterpret_cast<PipeSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * TG_COLS;
-    const bool chain = warp == 0;
-    constexpr unsigned TILE_BYTES = TG_ROWS * TG_COLS * (4 + 4 + 1);
+    const int col0 = blockIdx.x * PG_COLS;
+    constexpr unsigned SLICE_BYTES = PG_ROWS * PG_COLS * (4 + 4 + 1);
+    const int slices = (int)((T + PG_ROWS - 1) / PG_ROWS);      // slice j (processing order) = rows [(slices-1-j)*32, +32)
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&S.bar)));
+        for (int s = 0; s < PG_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&S.full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&S.dd[s])), "r"(PG_DWARPS * 32));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(smem_u32(&S.done[s])));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    float last = 0.0f;                                          // buffers.py:86
-    if (chain) {                                                // buffers.py:88 (t == T-1)
-        const float lv = col0 + lane < N ? last_values[col0 + lane] : 0.0f;
-        S.gvn[lane] = prescaled ? lv : __fmul_rn(gamma, lv);    // prescaled: already gamma*last_value (fp16 bootstrap)
     }
     __syncthreads();
 
-    const long long tiles = (T + TG_ROWS - 1) / TG_ROWS;
-    unsigned parity = 0;
-    for (long long k = tiles - 1; k >= 0; --k, parity ^= 1u) {
-        const int row0 = (int)(k * TG_ROWS);
-        const int rows = (int)(T - row0 < TG_ROWS ? T - row0 : TG_ROWS);
-        if (warp == 0 && elect_one()) {         // elect.sync: the TMA instructions issue without a divergence waterfall
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&S.bar)), "r"(TILE_BYTES) : "memory");
-            tma_load_2d(&S.r[0][0], &m_rewards, col0, row0, &S.bar);
-            tma_load_2d(&S.v[0][0], &m_values, col0, row0, &S.bar);
-            tma_load_2d(&S.d[0][0], &m_dones, col0, row0, &S.bar);
+    if (warp == 1 + PG_DWARPS) {
+        // ---- producer
+        if (elect_one()) {
+            // the store descriptors are first needed a few us into the kernel: fetch them now, off the critical path
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&m_adv) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&m_ret) : "memory");
+            auto load = [&](int j) {
+                PipeStage &st = S.st[j % PG_STAGES];
+                unsigned long long *bar = &S.full[j % PG_STAGES];
+                const int row0 = (slices - 1 - j) * PG_ROWS;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(SLICE_BYTES) : "memory");
+                tma_load_2d(&st.r[0][0], &m_rewards, col0, row0, bar);
+                tma_load_2d(&st.v[0][0], &m_values, col0, row0, bar);
+                tma_load_2d(&st.d[0][0], &m_dones, col0, row0, bar);
+            };
+            for (int j = 0; j < slices && j < PG_STAGES; ++j) load(j);
+            for (int j = 0; j < slices; ++j) {
+                const int s = j % PG_STAGES;
+                mbar_wait(&S.done[s], (unsigned)(j / PG_STAGES) & 1u);
+                const int row0 = (slices - 1 - j) * PG_ROWS;
+                tma_store_2d(&m_adv, col0, row0, &S.st[s].r[0][0]);
+                tma_store_2d(&m_ret, col0, row0, &S.st[s].v[0][0]);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (j + PG_STAGES < slices) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage's stores have read it
+                    load(j + PG_STAGES);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
-        {
-            unsigned done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(smem_u32(&S.bar)), "r"(parity) : "memory");
-        }
-        // ---- delta[t] = (r[t] + (gamma * v[t+1]) * nnt[t]) - v[t] (buffers.py:88-90) and c[t] =
-        // (gamma*lam) * nnt[t]: warp w owns rows w, w+4, ..., lane = column
-#pragma unroll 8
-        for (int i = warp; i < rows; i += TG_THREADS / 32) {
-            const float gv = i + 1 < rows ? __fmul_rn(gamma, S.v[i + 1][lane]) : S.gvn[lane];
-            const bool dn = S.d[i][lane] != 0;
-            S.r[i][lane] = __fsub_rn(__fadd_rn(S.r[i][lane], __fmul_rn(gv, dn ? 0.0f : 1.0f)), S.v[i][lane]);
-            S.c[i][lane] = dn ? 0.0f : gamma_lam;               // == gamma_lam * nnt exactly
-        }
-        __syncthreads();
-        // ---- chain: last = delta + c * last (buffers.py:91), 8 rows per batch read ahead of the dependent math
-        if (chain) {
-            S.gvn[lane] = __fmul_rn(gamma, S.v[0][lane]);       // for the tile before this one in time
-            for (int hi = rows; hi > 0; hi -= 8) {
-                float dl[8], gl[8];
+        return;
+    }
+
+    if (warp >= 1) {
+        // ---- delta warps: warp w owns rows w-1, w+2, ... of every slice, lane = column
+        const float lv = col0 + lane < N ? last_values[col0 + lane] : 0.0f;
+        float gvn = prescaled ? lv : __fmul_rn(gamma, lv);      // buffers.py:88 (t == T-1); prescaled: fp16 bootstrap
+        for (int j = 0; j < slices; ++j) {
+            PipeStage &st = S.st[j % PG_STAGES];
+            const int row0 = (slices - 1 - j) * PG_ROWS;
+            const int rows = (int)(T - row0 < PG_ROWS ? T - row0 : PG_ROWS);
+            mbar_wait(&S.full[j % PG_STAGES], (unsigned)(j / PG_STAGES) & 1u);
+            const float gvn_next = __fmul_rn(gamma, st.v[0][lane]);         // for the slice before this one in time
+            // delta[t] = (r[t] + (gamma * v[t+1]) * nnt[t]) - v[t] (buffers.py:88-90)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int i = hi - 1 - q >= 0 ? hi - 1 - q : 0;
-                    dl[q] = S.r[i][lane];
-                    gl[q] = S.c[i][lane];
+            for (int i = warp - 1; i < PG_ROWS; i += PG_DWARPS) {
+                if (i < rows) {
+                    const float gv = i + 1 < rows ? __fmul_rn(gamma, st.v[i + 1][lane]) : gvn;
+                    const float nn = st.d[i][lane] ? 0.0f : 1.0f;
+                    st.r[i][lane] = __fsub_rn(__fadd_rn(st.r[i][lane], __fmul_rn(gv, nn)), st.v[i][lane]);
+                }
+            }
+            gvn = gvn_next;
+            mbar_arrive(&S.dd[j % PG_STAGES]);
+        }
+        return;
+    }
+
+    // ---- walk warp: last = delta + ((gamma*lam) * nnt) * last (buffers.py:91) and returns = advantages + values
+    // (buffers.py:94); rows beyond `rows` (the ragged newest slice) are skipped
+    float last = 0.0f;                                          // buffers.py:86
+    for (int j = 0; j < slices; ++j) {
+        PipeStage &st = S.st[j % PG_STAGES];
+        const int row0 = (slices - 1 - j) * PG_ROWS;
+        const int rows = (int)(T - row0 < PG_ROWS ? T - row0 : PG_ROWS);
+        mbar_wait(&S.dd[j % PG_STAGES], (unsigned)(j / PG_STAGES) & 1u);
+        // BATCH rows of the column go to registers ahead of the dependent FMUL -> FADD chain.  BATCH = 32 (the whole
+        // slice, 96 loads in flight, 127 registers): the chain never waits for shared memory -- 5.2 instead of 6.2-7.1 us
+        // at T=128, N=8,192, where the walk is the critical path -- but only 3 CTAs fit an SM, which costs 9 % when
+        // the kernel is bandwidth-bound; BATCH = 8 (40 registers, 5 CTAs per SM) is the shape for many columns.
+        if (BATCH == PG_ROWS) {
+            float dl[PG_ROWS], gl[PG_ROWS], vv[PG_ROWS];
+#pragma unroll
+            for (int i = 0; i < PG_ROWS; ++i) {
+                dl[i] = st.r[i][lane];
+                gl[i] = st.d[i][lane] ? 0.0f : gamma_lam;                   // == gamma_lam * nnt exactly
+                vv[i] = st.v[i][lane];
+            }
+#pragma unroll
+            for (int i = PG_ROWS - 1; i >= 0; --i) {
+                if (i < rows) {
+                    last = __fadd_rn(dl[i], __fmul_rn(gl[i], last));
+                    st.r[i][lane] = last;
+                    st.v[i][lane] = __fadd_rn(last, vv[i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int hi = PG_ROWS; hi > 0; hi -= BATCH) {
+                float dl[BATCH], gl[BATCH], vv[BATCH];
+#pragma unroll
+                for (int q = 0; q < BATCH; ++q) {
+                    dl[q] = st.r[hi - 1 - q][lane];
+                    gl[q] = st.d[hi - 1 - q][lane] ? 0.0f : gamma_lam;      // == gamma_lam * nnt exactly
+                    vv[q] = st.v[hi - 1 - q][lane];
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < BATCH; ++q) {
                     const int i = hi - 1 - q;
-                    if (i >= 0) {
+                    if (i < rows) {
                         last = __fadd_rn(dl[q], __fmul_rn(gl[q], last));
-                        S.r[i][lane] = last;
+                        st.r[i][lane] = last;
+                        st.v[i][lane] = __fadd_rn(last, vv[q]);
                     }
                 }
             }
         }
-        __syncthreads();
-        // ---- returns = advantages + values (buffers.py:94), in place over the values
-#pragma unroll 8
-        for (int i = warp; i < rows; i += TG_THREADS / 32) S.v[i][lane] = __fadd_rn(S.r[i][lane], S.v[i][lane]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA store
-        __syncthreads();
-        if (warp == 0 && elect_one()) {
-            tma_store_2d(&m_adv, col0, row0, &S.r[0][0]);
-            tma_store_2d(&m_ret, col0, row0, &S.v[0][0]);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (k > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile buffers are reused
-        }
-        if (k > 0) __syncthreads();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(&S.done[j % PG_STAGES]);
     }
-    if (warp == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
@@ -291,12 +357,12 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// [T][N] row-major array of `es`-byte elements, box = [TG_ROWS][TG_COLS]
+// [T][N] row-major array of `es`-byte elements, box = [PG_ROWS][PG_COLS]
 static bool make_map(CUtensorMap *m, const void *base, CUtensorMapDataType dt, size_t es, int64_t T, int64_t N)
 {
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)T};
     const cuuint64_t strides[1] = {(cuuint64_t)N * es};
-    const cuuint32_t box[2] = {TG_COLS, TG_ROWS}, estr[2] = {1, 1};
+    const cuuint32_t box[2] = {PG_COLS, PG_ROWS}, estr[2] = {1, 1};
     return encode_tiled_fn()(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -339,9 +405,18 @@ extern "C" int msw_gae(const float *rewards, const float *values, const uint8_t 
             !make_map(&ma, advantages, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N) ||
             !make_map(&mt, returns, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N))
             return fail(MSW_ERR_ARG, "msw_gae: cuTensorMapEncodeTiled failed (T=%lld N=%lld)", (long long)T, (long long)N);
-        MSW_SET_MAX_SMEM(gae_tma_kernel, sizeof(TmaGaeSmem));
-        gae_tma_kernel<<<(unsigned)blocks, TG_THREADS, sizeof(TmaGaeSmem), (cudaStream_t)stream>>>(
-            mr, mv, md, ma, mt, last_values, T, N, gamma_f32, gamma_lam_f32, (int)last_values_prescaled);
+        // One wave of 3 CTAs per SM or less: latency-bound, the walk is the critical path -> the walk warp holds a
+        // whole slice column in registers (127 registers, 3 CTAs per SM).  More CTAs: bandwidth-bound -> 8-row
+        // batches (40 registers, 5 CTAs per SM); the register-heavy shape costs 9 % there (205 vs 186 us).
+        if (blocks <= 3LL * sm_count()) {
+            MSW_SET_MAX_SMEM(gae_pipe_kernel<PG_ROWS>, sizeof(PipeSmem));
+            gae_pipe_kernel<PG_ROWS><<<(unsigned)blocks, PG_THREADS, sizeof(PipeSmem), (cudaStream_t)stream>>>(
+                mr, mv, md, ma, mt, last_values, T, N, gamma_f32, gamma_lam_f32, (int)last_values_prescaled);
+        } else {
+            MSW_SET_MAX_SMEM(gae_pipe_kernel<8>, sizeof(PipeSmem));
+            gae_pipe_kernel<8><<<(unsigned)blocks, PG_THREADS, sizeof(PipeSmem), (cudaStream_t)stream>>>(
+                mr, mv, md, ma, mt, last_values, T, N, gamma_f32, gamma_lam_f32, (int)last_values_prescaled);
+        }
         MSW_CUDA_TRY(cudaGetLastError());
         return MSW_OK;
     }
