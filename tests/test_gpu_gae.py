@@ -41,10 +41,12 @@ def test_gae_matches_reference_fixtures():
         P.assert_bits_equal(ret, g[f"{name}_ret"], f"gae {name} ret (bit-exact)")
 
 
-# N % 16 == 0 takes the TMA kernel (incl. several 128-row tiles, a ragged last column box, T < one tile),
-# the other shapes the plain-load kernel
+# N % 16 == 0 takes the pipelined TMA kernel: more slices than ring stages (T > 128), a ragged newest slice
+# (T % 32 != 0), a ragged last column box (N % 32 != 0), T < one slice, and both launch shapes (the register-column
+# walk up to 3 CTAs per SM = 14,208 columns on 148 SMs, the 8-row-batch walk beyond); the other shapes take the
+# plain-load kernel
 @pytest.mark.parametrize("T,N", [(128, 8192), (64, 128), (300, 1000), (1, 1), (129, 33), (7, 65536), (300, 1024),
-                                 (128, 48), (5, 16), (257, 2000)])
+                                 (128, 48), (5, 16), (257, 2000), (100, 16384), (161, 32768), (32, 14208), (33, 14240)])
 def test_gae_matches_oracle(oracle, T, N):
     import torch
     rng = np.random.default_rng(T * 100003 + N)
