@@ -343,9 +343,10 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         for t in range(Wm):                    # warm up exactly as the timed loop runs: the previous result stays referenced
             pin = v.step_host(acts_host[t], copy_obs=copy_obs, copy_infos=False, threads=exp_threads)
         rows = [acts_host[Wm + t] for t in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); e1.record()               # events are created lazily at their first record: not inside the timed region
         barrier()
         t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         done_count = 0
         stamps = [t0]

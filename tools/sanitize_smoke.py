@@ -22,10 +22,11 @@ for (H, W, M, N) in [(16, 16, 40, 37), (16, 30, 99, 19), (5, 7, 6, 33), (32, 32,
     comp.gather_obs(torch.randperm(2 * N, device="cuda")[: N + 3])
     nv = m.VecMinesweeper(N, cfg, seed=1)                      # NumPy API / msw_step_host
     b = nv.reset()
-    nv.step(np.zeros(N, np.int32))
+    for t in range(3):                                         # recycled result sets: full write, then delta updates
+        b, _, _, _ = nv.step(np.full(N, t, np.int32))
     logits = torch.randn(N, H * W, device="cuda").half()
     m.masked_sample(logits, torch.rand(N, H * W, device="cuda") < 0.5, seed=1, step_index=2)
-for T, N in [(1, 1), (129, 33), (5, 70)]:
+for T, N in [(1, 1), (129, 33), (5, 70), (70, 48), (161, 16), (40, 16384)]:     # plain-load and both TMA launch shapes
     buf = m.RolloutBuffer(N, T, (1, 1, 1), 1, torch.device("cuda"))
     buf.rewards.normal_(); buf.values.normal_()
     buf.compute_gae(torch.randn(N, device="cuda"))
