@@ -173,6 +173,9 @@ class _LazyList(Sequence):
     def __repr__(self) -> str:
         return repr(list(self))
 
+    def __reduce__(self):                    # pickles (and copies) as the plain list it stands for
+        return (list, (list(self),))
+
 
 class _ResultSet:
     """One recycled (obs, mask) pair of the NumPy calling convention with the shadow msw_step_host's delta

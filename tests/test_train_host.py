@@ -103,3 +103,28 @@ def test_flat_grad_allreduce_keeps_replicas_identical_gloo(tmp_path):
     g = g * min(1.0, 0.5 / (float(g.norm()) + 1e-6))                  # clip_grad_norm_(0.5)
     expect = torch.cat([p.detach().reshape(-1) for p in m.parameters()]) - 0.1 * g
     assert torch.allclose(p0, expect, atol=1e-6)
+
+
+def test_lazy_infos_list_behaves_like_the_reference_list():
+    """VecMinesweeper.step's per-env infos lists (env.py:485-505) are lazy sequences: same indexing, slicing, len,
+    iteration and equality as the lists the reference builds; they pickle as plain lists."""
+    import copy
+    import pickle
+    from minesweeper_ppo_b200.env import _LazyList
+    made = []
+
+    def item(i):
+        made.append(i)
+        return {"step": i, "last_new_reveals": 2 * i, "revealed_frac": i / 8}
+
+    lz = _LazyList(5, item)
+    want = [{"step": i, "last_new_reveals": 2 * i, "revealed_frac": i / 8} for i in range(5)]
+    assert made == [] and len(lz) == 5                      # nothing is built until somebody looks
+    assert lz[3] == want[3] and lz[-1] == want[4] and made == [3, 4]
+    assert lz[1:4] == want[1:4] and list(lz) == want and lz == want and want == lz and not (lz != want)
+    assert lz != want[:4] and lz != [0] * 5 and (lz == "abcde") is False
+    assert int(lz[2].get("last_new_reveals", 0)) == 4       # the access pattern of eval.py:407-409
+    with pytest.raises(IndexError):
+        lz[5]
+    assert pickle.loads(pickle.dumps(lz)) == want and type(pickle.loads(pickle.dumps(lz))) is list
+    assert copy.deepcopy(lz) == want and repr(lz) == repr(want)
