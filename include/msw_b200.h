@@ -315,12 +315,15 @@ int msw_gn_act_bwd(const void *x16, const float *conv_bias, const float *gamma,
  *
  * obs / mask (the arrays VecMinesweeper.step returns, env.py:507-510: fp32
  * [n][10][H][W] and bool [n][HW]) are ORDINARY host memory and are not copied
- * over PCIe: the packed post-step state they are a pure function of (mines,
- * revealed, meta: 2*wpb + 4 words per env, 80 B instead of 10.5 KB at 16x16)
- * is copied into `stage` (pinned, n*(2*wpb + 4) int32) and expanded on
- * `threads` host threads (0 = every CPU the process may run on) after the
- * sync.  That is a format conversion of the GPU's result; no game logic runs
- * on the host. */
+ * over PCIe: the packed post-step state they are a pure function of (the mine
+ * and revealed bitboards: 2*wpb words per env, 64 B instead of 10.5 KB at
+ * 16x16; first_click_done is implied, see msw_expand_obs_host) is copied into
+ * `stage` (pinned, at least n*2*wpb int32: mines, then revealed) in up to
+ * four slices and expanded on `threads` host threads (0 = every CPU the
+ * process may run on), slice k while slices k+1.. are still on the bus.
+ * That is a format conversion of the GPU's result; no game logic runs on the
+ * host.  With `shadow` set only what changed since the arrays were last
+ * filled is rewritten (delta mode, below). */
 typedef struct msw_host_out {
     float   *obs;                  /* nullable; ordinary host memory */
     uint8_t *mask;                 /* nullable; ordinary host memory */

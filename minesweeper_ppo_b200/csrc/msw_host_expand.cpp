@@ -30,6 +30,7 @@
 #include <immintrin.h>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <sched.h>
 #include <stdint.h>
 #include <string.h>
@@ -48,8 +49,14 @@ class HostPool {
 public:
     static HostPool &get()
     {
-        static HostPool *p = new HostPool();      // intentionally leaked: workers may outlive static destruction
-        return *p;
+        // intentionally leaked: workers may outlive static destruction.  A fork()ed child inherits the object but
+        // none of its threads (a region would wait for workers that do not exist), so the child starts a fresh pool.
+        static std::once_flag once;
+        std::call_once(once, [] {
+            instance().store(new HostPool(), std::memory_order_release);
+            pthread_atfork(nullptr, nullptr, [] { instance().store(new HostPool(), std::memory_order_release); });
+        });
+        return *instance().load(std::memory_order_acquire);
     }
     // Runs fn(chunk) for chunk = 0..chunks-1 on up to `threads` threads (the caller is one of them).
     void run(int threads, long long chunks, const std::function<void(long long)> &fn)
@@ -81,6 +88,11 @@ public:
     }
 
 private:
+    static std::atomic<HostPool *> &instance()
+    {
+        static std::atomic<HostPool *> p{nullptr};
+        return p;
+    }
     static constexpr long long SPIN_US = 400;
     static void cpu_relax()
     {

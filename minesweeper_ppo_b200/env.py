@@ -657,11 +657,13 @@ class VecMinesweeper:
             res["obs"], res["mask"] = obs, mask
         else:
             h.obs = h.mask = None
-        if rset is not None and self.host_delta:               # delta mode: only what changed since this set was filled
+        use_shadow = rset is not None and self.host_delta
+        if use_shadow:                                         # delta mode: only what changed since this set was filled
             h.shadow, h.shadow_valid = rset.shadow.ctypes.data, rset.valid
-            rset.valid = 0                                     # until the call has succeeded
         else:
             h.shadow, h.shadow_valid = None, 0
+        if rset is not None:
+            rset.valid = 0                                     # until a call has succeeded WITH the shadow kept up to date
         h.threads = int(threads) if threads else self.host_threads
         io.inject_bits, io.inject_sel = ((self._inject[0].data_ptr(), self._inject[1].data_ptr())
                                          if self._inject is not None else (None, None))
@@ -672,7 +674,7 @@ class VecMinesweeper:
                 rc = self._L.msw_step_host(r_desc, r_state, r_io, ap, r_h, n, self._stream())
         if rc:
             _lib.check(rc, "msw_step_host")
-        if rset is not None:
+        if use_shadow:
             rset.valid = 1
         self._inject = None
         self._cache = None

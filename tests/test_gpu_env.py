@@ -79,6 +79,7 @@ def test_numpy_api_recycled_result_arrays(torch_cuda, oracle, H, W, M):
         sc[~b["action_mask"]] = -1
         a = sc.argmax(1) if t % 6 != 5 else rng.integers(0, HW, size=N)
         phase = t // 12
+        v.host_delta = not (phase == 1 and t % 4 == 1)          # a full rewrite now and then: its set's shadow goes stale
         if phase == 0:
             batch = None                                        # nothing referenced: one set, one step stale
         if phase == 2 and t % 3 == 0:
@@ -98,7 +99,7 @@ def test_numpy_api_recycled_result_arrays(torch_cuda, oracle, H, W, M):
         for rel, view, snap in held:
             assert np.array_equal(view, snap), f"a held result was overwritten at t={t}"
         held = [h for h in held if h[0] > t]
-    assert len(v._result_pool) >= 2 and all(e.valid for e in v._result_pool)
+    assert len(v._result_pool) >= 2 and any(e.valid for e in v._result_pool)
     assert int(cpu.episode_idx.max()) > 1
 
 

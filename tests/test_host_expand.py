@@ -128,3 +128,39 @@ def test_delta_expansion_requires_both_arrays(oracle):
     assert L.msw_expand_obs_host_delta(C.byref(desc), z.ctypes.data, z.ctypes.data, meta.ctypes.data, 4, obs.ctypes.data,
                                        None, sh.ctypes.data, 0, 1) != 0
     assert b"shadow" in L.msw_last_error()
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+def test_expansion_works_in_a_forked_child(oracle):
+    """The expander's worker threads do not survive fork(); a forked child (multiprocessing's default start method on
+    Linux) must get a fresh pool instead of waiting for threads it does not have."""
+    import os
+    from minesweeper_ppo_b200 import _lib
+    L = _lib.load()
+    N, H, W, HW = 2000, 16, 16, 256
+    rng = np.random.default_rng(1)
+    mine = rng.random((N, HW)) < 0.15
+    rev = (rng.random((N, HW)) < 0.4) & ~mine
+    pm, pr = _pack(mine, HW), _pack(rev, HW)
+    desc = _lib.EnvDesc(H, W, 40, 1, 0.0, 0.0, 0.0, 0, 0, 0)
+
+    def expand():
+        obs = np.empty((N, 10, H, W), np.float32)
+        mask = np.empty((N, HW), bool)
+        assert L.msw_expand_obs_host(C.byref(desc), pm.ctypes.data, pr.ctypes.data, None, N, obs.ctypes.data, mask.ctypes.data, 4) == 0
+        return obs, mask
+
+    want_obs, want_mask = expand()                       # the parent's pool now has worker threads
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            import signal
+            signal.alarm(20)                             # a child stuck on missing workers dies instead of hanging the suite
+            o, m = expand()
+            ok = 0 if (np.array_equal(o, want_obs) and np.array_equal(m, want_mask)) else 2
+        finally:
+            os._exit(ok)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
+    assert np.array_equal(want_mask, ~rev)
