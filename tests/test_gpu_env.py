@@ -103,6 +103,31 @@ def test_numpy_api_recycled_result_arrays(torch_cuda, oracle, H, W, M):
     assert int(cpu.episode_idx.max()) > 1
 
 
+def test_numpy_api_sliced_state_copy_at_scale(torch_cuda, oracle):
+    """From 32,768 envs on msw_step_host copies the packed state in four slices and expands slice k while the later
+    ones are still on the bus; 40,000 envs (ragged last slice) against the oracle, delta and full-rewrite modes."""
+    import os
+    import minesweeper_ppo_b200 as m
+    N, H, W, HW = 40000, 16, 16, 256
+    cfg = m.EnvConfig(H=H, W=W, mine_count=40, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    v = m.VecMinesweeper(N, cfg, seed=21)
+    cpu = oracle.OracleVecEnv(N, cfg, seed=21, nthreads=os.cpu_count() or 1)
+    rng = np.random.default_rng(4)
+    batch, b = v.reset(), cpu.reset()
+    for t in range(7):
+        sc = rng.random((N, HW), dtype=np.float32)
+        sc[~b["action_mask"]] = -1
+        a = sc.argmax(1)
+        v.host_delta = t != 4
+        batch, r, d, infos = v.step(a)
+        b, r0, d0, _ = cpu.step(a, tensor_infos=True)
+        P.assert_bits_equal(batch["obs"], b["obs"], f"t={t} obs")
+        P.assert_bits_equal(batch["action_mask"], b["action_mask"], f"t={t} mask")
+        P.assert_bits_equal(r, r0, f"t={t} rewards")
+        P.assert_bits_equal(d, d0, f"t={t} dones")
+        assert len(infos["aux"]) == N and infos["done"][N - 1] == bool(d0[N - 1])
+
+
 def test_cuda_floodfill_with_flags_matches_numba(torch_cuda):
     """Arbitrary (mines, revealed, flags, start) boards, including flags the hot path never sets."""
     import minesweeper_ppo_b200 as m
