@@ -139,6 +139,35 @@ class _EnvList:
         return (self[i] for i in range(len(self)))
 
 
+def _fastest_pinned(nbytes: int, dev_buf: torch.Tensor, to_host: bool, tries: int = 6) -> torch.Tensor:
+    """A pinned uint8 [nbytes] buffer for the small per-step DMAs of msw_step_host.  Where a pinned allocation lands in
+    host-physical memory decides how long a 256 KB DMA takes (17 us or 35 us for different 256 KB pieces of one
+    allocation on the GPU boxes, stable over time: profiles/r02aj_pinned_probe.txt), and these buffers are on the
+    critical path of every step, so `tries` candidates are allocated, one DMA is timed on each, and the fastest is kept
+    (about a millisecond, once per env)."""
+    import time
+    if nbytes == 0 or tries <= 1:
+        return torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+    cands = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(tries)]
+    stream = torch.cuda.current_stream(dev_buf.device)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        t = float("inf")
+        for rep in range(4):
+            stream.synchronize()
+            t0 = time.perf_counter()
+            if to_host:
+                c.copy_(dev_buf, non_blocking=True)
+            else:
+                dev_buf.copy_(c, non_blocking=True)
+            stream.synchronize()
+            if rep:                                   # the first copy of a buffer warms its translations
+                t = min(t, time.perf_counter() - t0)
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
 class _LazyList(Sequence):
     """A read-only list whose items are made on access (the per-env `infos` lists of VecMinesweeper.step,
     env.py:485-505).  Compares equal to the list / tuple / sequence with the same items."""
@@ -552,16 +581,17 @@ class VecMinesweeper:
                 off = (off + dt.itemsize - 1) // dt.itemsize * dt.itemsize
                 offs[k] = off
                 off += n * dt.itemsize
-            pin_blob = torch.empty((off,), dtype=torch.uint8).pin_memory()
             dev_blob = torch.empty((off,), dtype=torch.uint8, device=dev)
+            pin_blob = _fastest_pinned(off, dev_blob, to_host=True)
             for k, (shape, dt) in spec.items():
                 if k in offs:
                     nb = n * dt.itemsize
                     self._pinned[k] = pin_blob[offs[k]:offs[k] + nb].view(dt)
                     self._staging["h_" + k] = dev_blob[offs[k]:offs[k] + nb].view(dt)
                 else:
-                    self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
                     self._staging["h_" + k] = torch.empty(shape, dtype=dt, device=dev)
+                    self._pinned[k] = _fastest_pinned(n * dt.itemsize, self._staging["h_" + k].view(torch.uint8),
+                                                      to_host=False).view(dt)
             # packed post-step state (mines | revealed | meta): what obs / mask are expanded from on the host
             self._pinned["stage"] = torch.empty((n * (2 * self.wpb + 4),), dtype=torch.int32).pin_memory()
         return self._pinned, self._staging
