@@ -39,6 +39,11 @@ from . import _lib
 OBS_CHANNELS = _lib.OBS_CHANNELS
 _OUTCOME_NAMES = (None, "win", "loss")
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+try:
+    _libc = C.CDLL(None, use_errno=True)
+    _libc.madvise
+except Exception:                                             # pragma: no cover
+    _libc = None
 
 
 @dataclass
@@ -206,6 +211,20 @@ class _LazyList(Sequence):
         return (list, (list(self),))
 
 
+def _madvise_hugepage(a: np.ndarray) -> None:
+    """MADV_HUGEPAGE on the page-aligned interior of a large array (best effort; 2-3 % on the delta expansion where
+    transparent huge pages are in `madvise` mode, profiles/r02s_host_obs_probe.txt)."""
+    if a.nbytes < (4 << 20):
+        return
+    try:
+        lo = (a.ctypes.data + 4095) & ~4095
+        ln = (a.ctypes.data + a.nbytes - lo) & ~4095
+        if _libc is not None and ln > 0:
+            _libc.madvise(C.c_void_p(lo), C.c_size_t(ln), 14)             # MADV_HUGEPAGE
+    except Exception:
+        pass
+
+
 class _ResultSet:
     """One recycled (obs, mask) pair of the NumPy calling convention with the shadow msw_step_host's delta
     expansion keeps for it.  obs is 64-byte aligned (one board row of a 16-wide plane = one cache line)."""
@@ -219,6 +238,8 @@ class _ResultSet:
         self.mask = np.empty((n, H * W), bool)
         self.shadow = np.empty((n, max(1, shadow_words)), np.uint64)
         self.valid = 0                     # 0: obs / mask hold garbage; 1: exactly what `shadow` describes
+        for a in (self.raw, self.mask, self.shadow):       # scattered line updates: fewer TLB misses with huge pages
+            _madvise_hugepage(a)
 
 
 class VecMinesweeper:
