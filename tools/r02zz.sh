@@ -9,9 +9,3 @@ if grep -q "bench rc=0" gpurun_out/r02zz_bench.err; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r02zz_launches.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-train > gpurun_out/r02zz_ncu_bench.log 2>&1
 fi
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gae_pipe_kernel -s 86 -c 1 -o gpurun_out/r02zz_gae_large -f python tools/gae_sizes.py > gpurun_out/r02zz_ncu_gae_large.log 2>&1
-import json
-d = json.load(open("gpurun_out/r02zz_bench.json")); r = json.load(open("gpurun_out/r02zz_bench_reference.json"))
-print("value", d["value"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "host_obs", d["e2e_host_obs"]["value"], "ref", r["value"])
-print("rollout", d["rollout"]["frames_per_s"], "c4", d["c4"]["env_steps_per_s"], d["c4"]["frac_of_hbm_peak"], "c5", d["train_c5"]["frames_per_s"], "gae", d["gae"]["kernel_us"], d["gae"]["back_to_back_us"], d["gae"]["large"]["frac_of_hbm_peak"])
-print(d["e2e"]["step_ms"])
-P
