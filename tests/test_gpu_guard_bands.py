@@ -50,7 +50,9 @@ def test_env_outputs_stay_inside_their_windows(H, W, M, N):
     assert got.obs.shape[0] == N + 1
 
 
-@pytest.mark.parametrize("T,N", [(1, 1), (129, 33), (5, 70), (128, 31)])
+# ragged N: the plain-load kernel; N % 16 == 0: the TMA kernel, whose stores the tensor map clips (ragged slices and
+# column boxes, both launch shapes)
+@pytest.mark.parametrize("T,N", [(1, 1), (129, 33), (5, 70), (128, 31), (70, 48), (161, 16), (1, 16), (33, 14240)])
 def test_gae_outputs_stay_inside_their_windows(T, N):
     import torch
     import minesweeper_ppo_b200 as m
