@@ -57,6 +57,9 @@ struct EnvParams {
     uint32_t rk0, rk1, rand_step;
     int32_t *a_out;
     int vec_mode;                    // 1: 4 cells / lane, 128-bit stores (HW % 4 == 0); 0: scalar
+    // launch shape (launch_env): warps [0, wa) walk boards [0, na) with stride wa, warps [wa, wa + wb) walk
+    // boards [na, nb) with stride wb, the remaining warps own one board each of [nb, n)
+    long long seg_wa, seg_na, seg_wb, seg_nb;
     // per-lane geometry
     uint32_t g_valid[32], g_notcol0[32], g_notlast[32];
 };
@@ -309,7 +312,6 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
     const int HW = CHW ? CHW : p.HW;
     const int wpb = (HW + 31) >> 5;
     const long long warps_per_block = blockDim.x >> 5;
-    const long long total_warps = (long long)gridDim.x * warps_per_block;
     Geo g;
     g.valid = p.g_valid[lane];
     g.notcol0 = p.g_notcol0[lane];
@@ -317,12 +319,24 @@ __global__ void __launch_bounds__(256, MINB) env_kernel(const __grid_constant__ 
     const bool own = lane < wpb;
     const uint64_t keep = l2_keep_policy();
 
-    long long b = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (b >= p.n) return;
+    // Which boards this warp walks: b, b + stride, ... below `end` (three segments, see launch_env: late CTAs get
+    // fewer boards so that the grid drains over one board time instead of three)
+    const long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    long long b, end;
+    int stride;                                          // a segment never has more than 2^31 warps (grid limit)
+    if (w < p.seg_wa) {
+        b = w; stride = (int)p.seg_wa; end = p.seg_na;
+    } else if (w < p.seg_wa + p.seg_wb) {
+        b = p.seg_na + (w - p.seg_wa); stride = (int)p.seg_wb; end = p.seg_nb;
+    } else {
+        b = p.seg_nb + (w - p.seg_wa - p.seg_wb); stride = 1; end = b + 1 < p.n ? b + 1 : p.n;
+    }
+    if (b >= end) return;
+    int left = (int)((end - b + stride - 1) / stride);   // boards this warp walks (once per warp; keeps `end` out of the loop)
     BoardIn cur = load_board<MODE>(p, b, lane, wpb, keep);
     while (true) {
-        const long long nb = b + total_warps;
-        const bool more = nb < p.n;
+        const long long nb = b + stride;
+        const bool more = --left > 0;
         BoardIn nxt;
         if (PF && more) nxt = load_board<MODE>(p, nb, lane, wpb, keep);   // prefetch: consumed next iteration
 
@@ -901,12 +915,35 @@ static inline LaunchShape launch_shape_cfg()
 #endif
 }
 
-static inline int grid_for(long long n, int *block_out)
+// Fills the three launch segments of `q` and returns the grid.  Most warps walk `bpw` boards (next board's state
+// prefetched); CTAs are handed out in index order, so the LAST CTAs get two boards, then one: when the grid runs
+// out of CTAs the SMs otherwise drain over a whole 3-board CTA lifetime (~18 us of a 110 us launch at C2) with
+// falling occupancy; tapered, they drain over one board time.  Fluid picture: with S resident warps, S/3 of the
+// 3-board CTAs finish per board time, so S/3 two-board CTAs and then S/3 one-board CTAs keep every slot busy until
+// one board time before the end; board times vary, and twice that share measured best
+// (profiles/r02an_taper_sweep.txt, C2 kernel: no taper 109.8 us, 1x 107.7, 1.5x 106.9, 2x 106.7, 3x 107.3 us =
+// 6.27 -> 6.45 TB/s; C4, a 1.7 ms launch: 1710 -> 1705 us).
+static inline int grid_for(EnvParams &q, int resident_warps_per_sm, int *block_out)
 {
     const LaunchShape c = launch_shape_cfg();
     const int wpc = c.block / 32;
     *block_out = c.block;
-    const long long warps = (n + c.bpw - 1) / c.bpw;
+    const long long n = q.n;
+    long long taper_pct = 200;
+#ifdef MSW_DEV_KNOBS
+    if (const char *e = getenv("MSW_TAPER_PCT")) taper_pct = atoll(e);
+#endif
+    const long long S = (long long)sm_count() * resident_warps_per_sm;
+    long long n2 = 0, n1 = 0;                           // boards handled by 2-board and by 1-board warps
+    if (c.bpw >= 3 && n >= 4 * S && taper_pct > 0) {
+        n1 = S / 3 * taper_pct / 100;
+        n2 = 2 * n1;
+    }
+    q.seg_na = n - n2 - n1;
+    q.seg_wa = (q.seg_na + c.bpw - 1) / c.bpw;
+    q.seg_nb = q.seg_na + n2;
+    q.seg_wb = (n2 + 1) / 2;
+    const long long warps = q.seg_wa + q.seg_wb + n1;
     long long blocks = (warps + wpc - 1) / wpc;
     if (blocks < 1) blocks = 1;
     if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
@@ -925,11 +962,12 @@ static void launch_shape(const EnvParams &p, int grid, int block, cudaStream_t s
 }
 
 template <int MODE>
-static int launch_env(const EnvParams &p, cudaStream_t s)
+static int launch_env(const EnvParams &p_in, cudaStream_t s)
 {
-    if (p.n == 0) return MSW_OK;
+    if (p_in.n == 0) return MSW_OK;
+    EnvParams p = p_in;
     int block = 256;
-    const int grid = grid_for(p.n, &block);
+    const int grid = grid_for(p, MODE == MODE_STEP ? 24 : 32, &block);     // 80 / 64 registers: 24 / 32 one-warp CTAs per SM
     if (p.W == 16 && p.HW == 256)
         launch_shape<MODE, 16, 256>(p, grid, block, s);       // BASELINE configs 1-3, 5
     else if (p.W == 30 && p.HW == 480)
