@@ -935,7 +935,7 @@ static inline int grid_for(EnvParams &q, int resident_warps_per_sm, int *block_o
 #endif
     const long long S = (long long)sm_count() * resident_warps_per_sm;
     long long n2 = 0, n1 = 0;                           // boards handled by 2-board and by 1-board warps
-    if (c.bpw >= 3 && n >= 4 * S && taper_pct > 0) {
+    if (c.bpw >= 3 && n >= 8 * S && taper_pct > 0) {      // from eight waves on (measured at 18 and 148 waves)
         n1 = S / 3 * taper_pct / 100;
         n2 = 2 * n1;
     }
