@@ -16,14 +16,14 @@ import bench
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 out = []
-for name, board, n, ring in (("C2", (16, 16, 40), 65536, 4), ("C4", (16, 30, 99), 524288, 2)):
+for name, board, n, ring in ((("C2", (16, 16, 40), 65536, 4),) if os.environ.get("MSW_SWEEP_C2_ONLY") else (("C2", (16, 16, 40), 65536, 4), ("C4", (16, 30, 99), 524288, 2))):
     best = []
     for rep in range(3):
         ms_total, ms_kernel, clocks, _ = bench.time_env_steps(torch, m, dev, 0, 1, torch.cuda.synchronize, board, n, 40, 10, ring)
         best.append(ms_kernel)
     bytes_ = (41 * board[0] * board[1] + 9) * n
     out.append("%%s kernel %%.2f us (%%.0f GB/s; runs %%s)" %% (name, 1e3 * min(best), bytes_ / min(best) / 1e6, " ".join("%%.2f" %% (1e3 * b) for b in best)))
-print("taper_pct=%%s: " %% os.environ.get("MSW_TAPER_PCT") + "   ".join(out), flush=True)
+print("bpw=%%s taper_pct=%%s: " %% (os.environ.get("MSW_BPW"), os.environ.get("MSW_TAPER_PCT")) + "   ".join(out), flush=True)
 """ % (ROOT, DEV)
 
 if __name__ == "__main__":
@@ -34,7 +34,9 @@ if __name__ == "__main__":
         b.build_dev(DEV)
     if "--build" in sys.argv:
         sys.exit(0)
-    for pct in (0, 100, 0, 50, 100, 150, 200, 300, 0):
-        env = dict(os.environ, MSW_TAPER_PCT=str(pct))
+    combos = [(3, 200), (4, 200), (4, 300), (4, 400), (5, 300), (3, 200)] if "--bpw" in sys.argv else \
+             [(3, p_) for p_ in (0, 100, 0, 50, 100, 150, 200, 300, 0)]
+    for bpw, pct in combos:
+        env = dict(os.environ, MSW_TAPER_PCT=str(pct), MSW_BPW=str(bpw))
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "no output", flush=True)
