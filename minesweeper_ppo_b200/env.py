@@ -751,11 +751,14 @@ class VecMinesweeper:
             rewards = r.cpu().numpy()
         else:
             pin, _ = self._host_buffers()
-            a = actions.astype(np.int64, copy=False)
-            # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32
-            if a.size and (a.max() > 2**31 - 1 or a.min() < -2**31):
-                a = np.mod(a, self.HW)
-            pin["actions"].numpy()[:] = a
+            if actions.dtype.kind in "iu" and (actions.dtype.itemsize < 4 or actions.dtype == np.int32):
+                pin["actions"].numpy()[:] = actions               # fits int32 as it is: one conversion pass
+            else:
+                a = actions.astype(np.int64, copy=False)
+                # int(actions[i]) % (H*W) with Python semantics (env.py:104-106) for values beyond int32
+                if a.size and (a.max() > 2**31 - 1 or a.min() < -2**31):
+                    a = np.mod(a, self.HW)
+                pin["actions"].numpy()[:] = a
             res = self.step_host(pin["actions"])
             rewards = pin["reward"].numpy().copy()
             dones = pin["done"].numpy().copy()
