@@ -1,7 +1,6 @@
 """DMA time to / from different places of pinned host allocations (the ends of a large pinned allocation were seen to
 be ~45 us slower per 256 KB row than its middle in bench.py's e2e leg)."""
-import os, sys, time
-import numpy as np
+import time
 import torch
 
 dev = torch.device("cuda", 0)
