@@ -164,3 +164,47 @@ def test_expansion_works_in_a_forked_child(oracle):
     _, status = os.waitpid(pid, 0)
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
     assert np.array_equal(want_mask, ~rev)
+
+
+def test_worker_pool_under_changing_thread_counts_and_concurrent_callers(oracle):
+    """The expander's worker pool (spin, then sleep; one parallel region at a time): thread counts that change from
+    call to call (more threads than cores included), idle gaps long enough for the workers to fall asleep, and three
+    Python threads calling at once -- every call still produces the full, correct result."""
+    import threading
+    import time
+    from minesweeper_ppo_b200 import _lib
+    L = _lib.load()
+    N, H, W, HW = 1500, 16, 16, 256
+    rng = np.random.default_rng(2)
+    mine = rng.random((N, HW)) < 0.15
+    rev = (rng.random((N, HW)) < 0.4) & ~mine
+    pm, pr = _pack(mine, HW), _pack(rev, HW)
+    desc = _lib.EnvDesc(H, W, 40, 1, 0.0, 0.0, 0.0, 0, 0, 0)
+
+    def run(threads, obs, mask):
+        assert L.msw_expand_obs_host(C.byref(desc), pm.ctypes.data, pr.ctypes.data, None, N, obs.ctypes.data,
+                                     mask.ctypes.data, threads) == 0
+
+    want, wmask = np.empty((N, 10, H, W), np.float32), np.empty((N, HW), bool)
+    run(1, want, wmask)
+    assert np.array_equal(wmask, ~rev)
+    obs, mask = np.empty_like(want), np.empty_like(wmask)
+    for k in range(300):
+        obs.fill(-1.0)
+        run((1, 2, 3, 8, 16, 5, 32)[k % 7], obs, mask)
+        assert np.array_equal(obs, want) and np.array_equal(mask, wmask), k
+        if k % 60 == 0:
+            time.sleep(0.002)                                   # longer than the workers' spin: the wake-up path
+    bad = []
+
+    def caller():
+        o, m = np.empty_like(want), np.empty_like(wmask)
+        for k in range(100):
+            run((4, 7, 2)[k % 3], o, m)
+            if not (np.array_equal(o, want) and np.array_equal(m, wmask)):
+                bad.append(k)
+
+    threads = [threading.Thread(target=caller) for _ in range(3)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not bad
