@@ -128,15 +128,18 @@ class ClockSampler(threading.Thread):
                 self.reasons.add(name)
 
     def run(self):
+        # The first sample is taken one period AFTER the start: an NVML query issued while the main thread is still
+        # queueing the first launches contends with it for the driver and starves the GPU between launches (20 timed
+        # launches measured 108.6 us per step with a sample at t = 0, 103.6 us steady state in tools/warm_probe.py).
+        # A region shorter than one period gets its sample from finish(), which runs while the GPU is still busy.
         if self.nv is None:
             return
-        while not self._stop_evt.is_set():
+        while not self._stop_evt.wait(self.period):
             try:
                 self.sample_once()
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 break
-            self._stop_evt.wait(self.period)
 
     def finish(self):
         """Call while the GPU is still busy with the timed region (before the final synchronize), so
@@ -234,11 +237,11 @@ def run_reference_arm(args, rank: int, world: int):
 
 
 # ----------------------------------------------------------------------------- CUDA arm
-def time_env_steps(torch, m, dev, rank, world, barrier, board, n_envs, K, Wm, ring, valid_only=True, keep_actions=0):
-    """The device-timed leg for one board/env-count: W untimed + K timed fused step launches (built-in
-    synthetic policy), CUDA events around the K launches only; then a separate replay of up to 64 more
-    launches with an event pair around EACH launch (per-launch kernel time for the roofline) -- no event
-    pair sits inside the timed region."""
+def time_env_steps(torch, m, dev, rank, world, barrier, board, n_envs, K, Wm, ring, valid_only=True):
+    """The device-timed leg for one board/env-count: PRE_ROLL + W untimed and K timed fused step launches (built-in
+    synthetic policy), CUDA events around the K launches only; then a separate replay that measures the per-launch
+    kernel time for the roofline (back to back between one event pair, and with an event pair around each launch).
+    Returns (ms of the K timed launches, kernel ms back to back, clocks, kernel ms bracketed)."""
     h, w, mines = board
     cfg = m.EnvConfig(H=h, W=w, mine_count=mines, guarantee_safe_neighborhood=True, step_penalty=1e-4)
     vec = m.VecMinesweeper(n_envs, cfg, seed=0, api="torch", env_id_base=rank * n_envs)
@@ -246,36 +249,67 @@ def time_env_steps(torch, m, dev, rank, world, barrier, board, n_envs, K, Wm, ri
                        action_mask=torch.empty((n_envs, h * w), dtype=torch.bool, device=dev),
                        rewards=torch.empty((n_envs,), dtype=torch.float32, device=dev),
                        dones=torch.empty((n_envs,), dtype=torch.bool, device=dev)) for _ in range(ring)]
-    log = torch.empty((Wm + keep_actions + 1, n_envs), dtype=torch.int32, device=dev) if keep_actions else None
     scratch = torch.empty((n_envs,), dtype=torch.int32, device=dev)
     vec.reset(out=slots[0])
     for t in range(PRE_ROLL):                                    # workload setup: stationary mix of episode phases
         vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
-    Wm0, Wm = Wm, Wm + PRE_ROLL                                  # step indices continue after the pre-roll
+    Wm = Wm + PRE_ROLL                                           # step indices continue after the pre-roll
     for t in range(PRE_ROLL, Wm):
-        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=log[t - PRE_ROLL] if keep_actions else scratch)
+        vec.step_random(t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(torch, dev.index)
     barrier()
     sampler.start()
     ev0.record()
     for t in range(K):
-        a = log[Wm0 + min(t, keep_actions)] if keep_actions else scratch
-        vec.step_random(Wm + t, valid_only=valid_only, out=slots[t % ring], actions_out=a)   # policy + step: one launch
+        vec.step_random(Wm + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)   # policy + step: one launch
     ev1.record()
     clocks = sampler.finish()          # sampled while the last launches are still executing
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    # Per-launch kernel time for the roofline, from a separate replay after the timed region: Kk launches back to back
+    # between ONE event pair (launches of one stream do not overlap, so elapsed / Kk bounds the mean kernel duration
+    # from above), after 5 launches that absorb the restart after the barrier.  An event pair around EACH launch adds
+    # ~2 us of front-end gap to every launch (`bracketed`, kept for reference).
     Kk = min(64, max(8, K))
+    for t in range(5):
+        vec.step_random(Wm + K + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for t in range(Kk):
+        vec.step_random(Wm + K + 5 + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
+    r1.record()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
     for t in range(Kk):
         kev[t][0].record()
-        vec.step_random(Wm + K + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
+        vec.step_random(Wm + K + 5 + Kk + t, valid_only=valid_only, out=slots[t % ring], actions_out=scratch)
         kev[t][1].record()
     barrier()
-    ms_kernel = float(np.mean([x.elapsed_time(y) for x, y in kev]))
+    ms_kernel = r0.elapsed_time(r1) / Kk
+    ms_kernel_bracketed = float(np.mean([x.elapsed_time(y) for x, y in kev]))
     del vec, slots
-    return ms_total, ms_kernel, clocks, log
+    return ms_total, ms_kernel, clocks, ms_kernel_bracketed
+
+
+def record_actions(torch, m, dev, rank, board, n_envs, steps, valid_only=True):
+    """int32 [steps, n_envs]: the built-in synthetic policy's actions for `steps` steps after reset() + PRE_ROLL
+    steps (the trajectory the e2e legs replay through msw_step_host)."""
+    h, w, mines = board
+    cfg = m.EnvConfig(H=h, W=w, mine_count=mines, guarantee_safe_neighborhood=True, step_penalty=1e-4)
+    vec = m.VecMinesweeper(n_envs, cfg, seed=0, api="torch", env_id_base=rank * n_envs)
+    out = m.StepOut(obs=torch.empty((n_envs, 10, h, w), dtype=torch.float32, device=dev),
+                    action_mask=torch.empty((n_envs, h * w), dtype=torch.bool, device=dev),
+                    rewards=torch.empty((n_envs,), dtype=torch.float32, device=dev),
+                    dones=torch.empty((n_envs,), dtype=torch.bool, device=dev))
+    log = torch.empty((steps, n_envs), dtype=torch.int32, device=dev)
+    scratch = torch.empty((n_envs,), dtype=torch.int32, device=dev)
+    vec.reset(out=out)
+    for t in range(PRE_ROLL):
+        vec.step_random(t, valid_only=valid_only, out=out, actions_out=scratch)
+    for t in range(steps):
+        vec.step_random(PRE_ROLL + t, valid_only=valid_only, out=out, actions_out=log[t])
+    torch.cuda.synchronize()
+    return log
 
 
 def run_cuda_arm(args, rank: int, world: int, local_rank: int):
@@ -314,8 +348,12 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         return [float(o.item()) for o in out]
 
     Ke = min(K, 400)                           # steps replayed by the e2e legs
-    ms_total, ms_kernel, clocks, actions_log = time_env_steps(torch, m, dev, rank, world, barrier, (H, W, MINES), N, K, Wm,
-                                                              ring, VALID_ONLY, keep_actions=Ke)
+    ms_total, ms_kernel, clocks, ms_kernel_bracketed = time_env_steps(torch, m, dev, rank, world, barrier, (H, W, MINES),
+                                                                      N, K, Wm, ring, VALID_ONLY)
+    # The actions the e2e legs replay are recorded in a separate untimed pass over the same deterministic trajectory
+    # (recording inside the timed launches costs 3 us per launch: 65,536 four-byte stores into a row of device memory
+    # that is cold every step, against a scratch row that stays in L2).
+    actions_log = record_actions(torch, m, dev, rank, (H, W, MINES), N, Wm + Ke, VALID_ONLY)
     episodes = None
 
     # -- e2e: same workload through the host-buffer C-ABI call (msw_step_host): per step, this
@@ -415,10 +453,17 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
         "roofline": {
             "bound": "hbm", "kernel": f"msw::env_kernel<MODE_STEP,{W},{H * W}>", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "peak_note": "hbm_gbs is a read+write copy; this kernel only writes, and write-only streams reach 6.9-7.0 TB/s "
+                         "on this part (profiles/r01_store_probe2.txt), so a fraction near or slightly above 1.0 of the "
+                         "copy peak is the practical ceiling",
             "algorithmic_bytes_per_launch": BYTES_PER_STEP * N, "kernel_ms": ms_kernel_max,
             "kernel_ms_per_rank": kernel_ms_ranks,
-            "kernel_ms_how": "mean over a separate replay of launches, one CUDA-event pair per launch, after the timed "
-                             "region (no event pairs inside it); max over ranks",
+            "kernel_ms_how": "separate replay after the timed region: min(64, K) launches back to back between one CUDA-event "
+                             "pair, elapsed / count (launches of one stream do not overlap, so this bounds the mean kernel duration "
+                             "from above); max over ranks",
+            "kernel_ms_bracketed": ms_kernel_bracketed,
+            "kernel_ms_bracketed_how": "the same replay with an event pair around EACH launch (adds ~2 us of front-end "
+                                       "gap per launch); rank 0",
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),
         },
