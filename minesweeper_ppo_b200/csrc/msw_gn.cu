@@ -538,7 +538,7 @@ extern "C" int msw_gn_act(const void *x16, const float *conv_bias, const float *
     p.pool = pool32;
     p.sample_base = (long long)sample_id_base;
     p.tile_bytes = (unsigned)tile_bytes;
-    p.bulk = 1;      // one cp.async.bulk per sample (the per-thread cp.async / STG path measured 6 % slower: profiles/r01g_gn_bulk.txt)
+    p.bulk = 1;      // one cp.async.bulk per sample (the per-thread cp.async / STG path measured 6 % slower in round 1)
     if ((save_mean != nullptr) != (save_rstd != nullptr) || (save_mean != nullptr) != (save_mask != nullptr))
         return fail(MSW_ERR_ARG, "msw_gn_act: save_mean / save_rstd / save_mask must be given together");
     p.save_mean = save_mean; p.save_rstd = save_rstd; p.save_mask = save_mask;
