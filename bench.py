@@ -359,10 +359,11 @@ def run_cuda_arm(args, rank: int, world: int, local_rank: int):
     # -- e2e: same workload through the host-buffer C-ABI call (msw_step_host): per step, this
     # step's actions come from pinned host memory (H2D) and rewards+dones go back to pinned host
     # memory (D2H); obs/mask land in device memory where the policy consumes them.
-    # The recorded actions live in ONE pinned allocation, a different 256 KB row per step.  Rows in the first and last
-    # 2 MB of such an allocation were measured 45 us slower to DMA (steps 17-19 of 20 in profiles/r02ah_*: the ends of a
-    # pinned allocation are not huge-page backed, so every new row there costs 64 IOMMU translations); a real caller
-    # reuses one small, translation-warm buffer.  Hence 2 MB of padding on either side of the rows that are used.
+    # The recorded actions live in ONE pinned allocation, a different 256 KB row per step.  How long a 256 KB DMA takes
+    # depends on where the piece of pinned memory lies physically (17 us or 25-36 us, profiles/r02aj_pinned_probe.txt);
+    # the last three rows of the unpadded allocation were slow ones (+45 us on steps 17-19 of 20 in
+    # profiles/r02ah_bench_e2e_tail_rows.json), the middle rows of a padded allocation have been uniformly fast in every
+    # run since.  Hence 2 MB of padding on either side of the rows that are used.
     pad = max(1, (2 << 20) // (4 * N))
     acts_pinned = torch.empty((Wm + Ke + 2 * pad, N), dtype=torch.int32).pin_memory()
     acts_host = acts_pinned[pad:pad + Wm + Ke]
